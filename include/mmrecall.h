@@ -1,0 +1,165 @@
+/*
+ * mmrecall.h — C ABI of the B200-native (sm_100a) cross-modal match scorer.
+ *
+ * The reference (zuokai/KDDCUP_2020_MultimodalitiesRecall_2nd_Place) has no FFI layer: its hot path is
+ * reached through Python calls into TensorFlow-1 / PyTorch-1 stock ops.  This header is the boundary a
+ * maintainer binds instead (ctypes stub in INTEGRATION.md).  Each entry point names the reference
+ * call site it replaces.  Plain pointers and sizes only; no torch / C++ types cross this ABI.
+ *
+ * Conventions
+ *   - every pointer marked "dev" is a device pointer valid on the current CUDA device;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - calls are asynchronous w.r.t. the host, ordered on `stream`; nothing here synchronises;
+ *   - 16-bit operands are bf16 (MMR_DT_BF16) or fp16 (MMR_DT_FP16); accumulation, LayerNorm statistics,
+ *     softmax and the residual stream are fp32;
+ *   - weights are [out, in] row-major ("K-major"), i.e. torch nn.Linear.weight; a TF `kernel` [in,out]
+ *     is transposed by the packer (mmr_create does it for you);
+ *   - return value: MMR_OK or an error code, with text in mmr_last_error(); no exceptions cross the ABI;
+ *   - there is NO CPU fallback: on a device that is not sm_100 every entry returns MMR_ERR_ARCH.
+ */
+#ifndef MMRECALL_H_
+#define MMRECALL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  MMR_OK = 0,
+  MMR_ERR_INVALID = 1, /* bad argument: shape / alignment / null pointer            */
+  MMR_ERR_CUDA = 2,    /* a CUDA runtime / driver call failed                        */
+  MMR_ERR_ARCH = 3,    /* device is not sm_100 (B200); no fallback path exists       */
+  MMR_ERR_NOMEM = 4,   /* device allocation failed                                   */
+  MMR_ERR_WEIGHTS = 5  /* a required weight tensor is missing or has the wrong shape */
+} mmr_status;
+
+typedef enum { MMR_DT_FP16 = 0, MMR_DT_BF16 = 1 } mmr_dtype;
+
+typedef enum {
+  MMR_ACT_NONE = 0,
+  MMR_ACT_RELU = 1,      /* slim.conv2d default activation: imagebert_zk/model_triple.py:189,193 */
+  MMR_ACT_GELU_TANH = 2, /* imagebert_zk/pixelbert.py:315-328                                   */
+  MMR_ACT_GELU_ERF = 3,  /* lxmert/src/lxrt/modeling.py:113-119                                 */
+  MMR_ACT_TANH = 4       /* pooler: pixelbert.py:258-266, modeling.py:596-608                   */
+} mmr_act;
+
+typedef enum {
+  MMR_MODEL_IMAGEBERT_ZK = 0,  /* code/imagebert_zk  (ImageBertB / C) */
+  MMR_MODEL_IMAGEBERT_LDS = 1, /* code/imagebert_lds (ImageBertA)     */
+  MMR_MODEL_LXMERT = 2         /* code/lxmert                          */
+} mmr_model_kind;
+
+const char* mmr_last_error(void);
+int mmr_abi_version(void);
+/* MMR_OK iff `device` is an sm_100 part. */
+mmr_status mmr_device_check(int device);
+
+/* ------------------------------------------------------------------------------------------------
+ * Operator level (one kernel each).  Used by the model driver below and by the parity tests.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* out = act(A[M,K] * W[N,K]^T + bias) (+ residual).  tcgen05 tensor-core GEMM, TMA-fed, fp32 accumulate
+ * in TMEM.  Replaces tf.layers.dense / slim.fully_connected / nn.Linear at pixelbert.py:767-788, 960-985;
+ * pixelmodel.py:439-442; modeling.py:325-420, 522-523.
+ *   A16   dev, 16-bit, row stride lda (elements; lda*2 bytes must be a multiple of 16)
+ *   W16   dev, 16-bit [N,K], row stride ldw
+ *   bias  dev fp32 [N] or NULL;  residual dev fp32 [M, ldr] or NULL (added after the activation)
+ *   out16 dev 16-bit [M, ldo16] or NULL;  out32 dev fp32 [M, ldo32] or NULL (at least one required)
+ * K must be a multiple of 64, N a multiple of 16. */
+mmr_status mmr_gemm(const void* A16, int64_t lda, const void* W16, int64_t ldw, int M, int N, int K,
+                    const float* bias, const float* residual, int64_t ldr, void* out16, int64_t ldo16,
+                    float* out32, int64_t ldo32, int act, int dtype, void* stream);
+
+/* Row LayerNorm over the last dim (biased variance, eps inside the sqrt): tf.contrib.layers.layer_norm
+ * (pixelbert.py:414-417) / nn.LayerNorm(eps=1e-12) (modeling.py:266).  x fp32 [M, ldx]; writes the
+ * normalised row as 16-bit (GEMM operand) and/or fp32 (residual stream); `scale` multiplies the result
+ * (LXMERT's "/3", modeling.py:530); accumulate!=0 adds into out32 instead of overwriting. */
+mmr_status mmr_layernorm(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, int M,
+                         int H, void* out16, int64_t ldo16, float* out32, int64_t ldo32, float scale,
+                         int accumulate, int dtype, void* stream);
+
+/* Multi-head scaled-dot-product attention, softmax in fp32, additive key mask (1-m)*-10000:
+ * pixelbert.py:790-850 / modeling.py:325-352.  q [B*Sq, ldq], k/v [B*Sk, ldk/ldv], head h = columns
+ * [64h, 64h+64).  key_mask dev int32 [B,Sk] (1 = attend) or NULL.  Sq, Sk <= 128. */
+mmr_status mmr_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                         const int32_t* key_mask, void* out16, int64_t ldo, int B, int Sq, int Sk,
+                         int heads, int dtype, void* stream);
+
+/* fp32 -> 16-bit cast with 16-byte vector loads (region features [B*R,2048]). n must be a multiple of 8. */
+mmr_status mmr_cast16(const float* x, void* out16, int64_t n, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Model level.
+ * ---------------------------------------------------------------------------------------------- */
+
+typedef struct mmr_handle mmr_handle;
+
+typedef struct {
+  int32_t model_kind;   /* mmr_model_kind                                                         */
+  int32_t dtype;        /* mmr_dtype of the MMA operands                                          */
+  int32_t hidden;       /* 768  (user_data/bert_config.json)                                      */
+  int32_t heads;        /* 12                                                                     */
+  int32_t intermediate; /* 3072                                                                   */
+  int32_t vocab;        /* 21128                                                                  */
+  int32_t max_pos;      /* 512                                                                    */
+  int32_t type_vocab;   /* 2                                                                      */
+  int32_t feat_dim;     /* 2048                                                                   */
+  int32_t label_len;    /* 8 label-text tokens per box                                            */
+  int32_t n_layers;     /* single-stream encoder depth (zk / lds); LXMERT: language layers        */
+  int32_t n_r_layers;   /* LXMERT relational (visual) layers, else 0                              */
+  int32_t n_x_layers;   /* LXMERT cross-modality layers, else 0                                   */
+  int32_t lq;           /* query tokens  (reference native: 20 zk/lds, 23 lxmert)                 */
+  int32_t nbox;         /* region slots  (reference native: 10)                                   */
+  int32_t max_batch;    /* workspace is sized for this many pairs per forward                     */
+} mmr_config;
+
+/* One named fp32 host tensor, named exactly as in the reference checkpoint (TF variable name or torch
+ * state_dict key). */
+typedef struct {
+  const char* name;
+  const float* data; /* host */
+  int32_t ndim;
+  int64_t dims[4];
+} mmr_tensor;
+
+/* Device inputs of one forward over B pairs.  Shapes follow the reference feeds:
+ * evaluate_normal.py:141-152 (zk), run_pretraining_predict_score.py:526-541 (lds), kdd_model.py:74-100
+ * (lxmert).  Unused members may be NULL. */
+typedef struct {
+  const int32_t* query_ids;   /* [B, lq]                                                          */
+  const int32_t* segment_ids; /* zk: [B, lq+nbox]; lds: [B, lq]; lxmert: NULL (all 0)              */
+  const int32_t* label_ids;   /* [B, nbox, label_len]                                             */
+  const float* feats;         /* [B, nbox, feat_dim] fp32                                         */
+  const float* boxes;         /* zk: [B, nbox, 5]; lxmert: [B, nbox, 4]; lds: unused              */
+  const int32_t* len_query;   /* zk: [B]   (tf.sequence_mask, model_triple.py:198)                */
+  const int32_t* num_boxes;   /* zk: [B]   (model_triple.py:199)                                  */
+  const int32_t* query_mask;  /* lxmert: [B, lq]  input_mask                                      */
+  const int32_t* visn_mask;   /* lxmert: [B, nbox] visual_attention_mask                          */
+  const int32_t* labels;      /* zk: [B] AM-softmax margin label (model_triple.py:66-81)          */
+} mmr_inputs;
+
+mmr_status mmr_create(const mmr_config* cfg, const mmr_tensor* weights, int n_weights, int device,
+                      mmr_handle** out);
+void mmr_destroy(mmr_handle* h);
+
+/* Scores B pairs (B <= max_batch).  probs_out dev fp32 [B,2] (softmax of the 2-way head; the reference
+ * score is column 1 — for LXMERT column -1, same thing).  pooled_out dev fp32 [B,hidden] or NULL.
+ * Replaces model_triple.model_attention_channel_e (model_triple.py:162-214), bertmodel(...) inference
+ * path (run_pretraining_predict_score.py:288-394) and KDDModel.forward (kdd_model.py:183-214). */
+mmr_status mmr_forward(mmr_handle* h, const mmr_inputs* in, int B, float* probs_out, float* pooled_out,
+                       void* stream);
+
+/* Debug / parity taps: copies of internal activations after the last forward (dev fp32).
+ * which: 0 = embedding output [B*S, hidden]; 1 = final encoder layer output (lang stream for LXMERT). */
+mmr_status mmr_get_activation(mmr_handle* h, int which, float* dst, int64_t n_floats, void* stream);
+
+/* Number of kernels one mmr_forward launches for batch B (for bench.py's gpu_launches claim). */
+int mmr_launches_per_forward(const mmr_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMRECALL_H_ */

@@ -1,0 +1,249 @@
+// Multi-head scaled-dot-product attention for the short sequences of this workload (Sq, Sk <= 128, d = 64).
+//
+// Replaces pixelbert.py:790-850 (transpose_for_scores, QK^T / sqrt(d), additive mask, softmax, PV, merge heads)
+// and lxmert modeling.py:325-352 (BertAttention, self- and cross-), i.e. everything between the QKV projection
+// and the output projection.  ~1.5 % of the layer FLOPs: one CTA per (pair, head) keeps Q, K, V of that head in
+// shared memory, each warp owns 16 query rows, scores / softmax stay in fp32 registers, the two small matmuls
+// run on the warp-level tensor path (mma.sync m16n8k16, fp32 accumulate).  Semantics kept from the reference:
+// additive key mask (1 - m) * -10000 (NOT -inf), queries never masked, softmax over keys in fp32.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace mmr {
+
+constexpr int kHeadDim = 64;
+constexpr int kPitch = 72;       // smem row pitch in elements (144 B): conflict-free ldmatrix
+constexpr int kMaxSeq = 128;
+constexpr int kMaxKT = kMaxSeq / 8;
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
+                                                  uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+template <class E16>
+__device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                          uint32_t b0, uint32_t b1) {
+  if constexpr (E16::kFmt == MMR_DT_BF16) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  } else {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  }
+}
+
+template <class E16>
+__global__ void __launch_bounds__(256)
+attention_kernel(const typename E16::T* __restrict__ q, int64_t ldq, const typename E16::T* __restrict__ k,
+                 int64_t ldk, const typename E16::T* __restrict__ v, int64_t ldv,
+                 const int32_t* __restrict__ key_mask, typename E16::T* __restrict__ out, int64_t ldo, int Sq,
+                 int Sk) {
+  using T = typename E16::T;
+  extern __shared__ __align__(16) uint8_t smem_att[];
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int nwarps = blockDim.x >> 5;
+  const int SqP = nwarps * 16;
+  const int SkP = (Sk + 15) & ~15;
+  T* sQ = reinterpret_cast<T*>(smem_att);
+  T* sK = sQ + SqP * kPitch;
+  T* sV = sK + SkP * kPitch;
+  float* sMask = reinterpret_cast<float*>(sV + SkP * kPitch);  // [SkP] additive mask
+
+  // ---- cooperative load of this (pair, head): 8 x 16-byte chunks per 64-wide row, zero padding rows ----
+  const int tid = threadIdx.x;
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < SqP * 8; i += blockDim.x) {
+    const int r = i >> 3, c = (i & 7) * 8;
+    uint4 val = zero4;
+    if (r < Sq) val = *reinterpret_cast<const uint4*>(q + (int64_t(b) * Sq + r) * ldq + h * kHeadDim + c);
+    *reinterpret_cast<uint4*>(sQ + r * kPitch + c) = val;
+  }
+  for (int i = tid; i < SkP * 8; i += blockDim.x) {
+    const int r = i >> 3, c = (i & 7) * 8;
+    uint4 kv = zero4, vv = zero4;
+    if (r < Sk) {
+      kv = *reinterpret_cast<const uint4*>(k + (int64_t(b) * Sk + r) * ldk + h * kHeadDim + c);
+      vv = *reinterpret_cast<const uint4*>(v + (int64_t(b) * Sk + r) * ldv + h * kHeadDim + c);
+    }
+    *reinterpret_cast<uint4*>(sK + r * kPitch + c) = kv;
+    *reinterpret_cast<uint4*>(sV + r * kPitch + c) = vv;
+  }
+  for (int i = tid; i < SkP; i += blockDim.x) {
+    float m = -INFINITY;  // padding keys (>= Sk) do not exist for the softmax
+    if (i < Sk) m = (key_mask == nullptr || key_mask[int64_t(b) * Sk + i] != 0) ? 0.0f : -10000.0f;
+    sMask[i] = m;
+  }
+  __syncthreads();
+
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int q0 = warp * 16;
+  if (q0 >= Sq) return;
+  const int nkt = SkP >> 3;   // 8-key score tiles
+  const int nks = SkP >> 4;   // 16-key steps for P.V
+
+  // ---- S = Q K^T (fp32 accumulate) ----
+  uint32_t qa[4][4];
+  {
+    // A fragment rows: lanes 0-15 -> rows q0 + lane (cols +0), lanes 16-31 -> rows q0 + lane-16 (cols +8)
+    const int r = q0 + (lane & 15), cofs = (lane >> 4) * 8;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      ldmatrix_x4(smem_u32(sQ + r * kPitch + ks * 16 + cofs), qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
+    }
+  }
+  float s[kMaxKT][4];
+#pragma unroll
+  for (int nt = 0; nt < kMaxKT; ++nt) { s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f; }
+#pragma unroll
+  for (int np = 0; np < kMaxKT / 2; ++np) {
+    if (np * 2 < nkt) {
+      // B fragments for keys [16np, 16np+16): matrices (keys 0-7, d lo), (keys 0-7, d hi), (keys 8-15, d lo), (.., d hi)
+      const int kr = np * 16 + (lane & 7) + ((lane >> 4) << 3);
+      const int dofs = ((lane >> 3) & 1) * 8;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t b0, b1, b2, b3;
+        ldmatrix_x4(smem_u32(sK + kr * kPitch + ks * 16 + dofs), b0, b1, b2, b3);
+        mma_16816<E16>(s[2 * np], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b0, b1);
+        mma_16816<E16>(s[2 * np + 1], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b2, b3);
+      }
+    }
+  }
+
+  // ---- scale, additive mask, softmax over keys (rows g and g+8 of this warp's 16) ----
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < kMaxKT; ++nt) {
+    if (nt < nkt) {
+      const float m0 = sMask[nt * 8 + 2 * t4], m1 = sMask[nt * 8 + 2 * t4 + 1];
+      s[nt][0] = fmaf(s[nt][0], 0.125f, m0);
+      s[nt][1] = fmaf(s[nt][1], 0.125f, m1);
+      s[nt][2] = fmaf(s[nt][2], 0.125f, m0);
+      s[nt][3] = fmaf(s[nt][3], 0.125f, m1);
+      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+    }
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  float sum0 = 0.f, sum1 = 0.f;
+  uint32_t pa[kMaxKT][2];  // P as 16-bit A fragments
+#pragma unroll
+  for (int nt = 0; nt < kMaxKT; ++nt) {
+    if (nt < nkt) {
+      const float e0 = __expf(s[nt][0] - mx0), e1 = __expf(s[nt][1] - mx0);
+      const float e2 = __expf(s[nt][2] - mx1), e3 = __expf(s[nt][3] - mx1);
+      sum0 += e0 + e1;
+      sum1 += e2 + e3;
+      pa[nt][0] = E16::pack(e0, e1);
+      pa[nt][1] = E16::pack(e2, e3);
+    }
+  }
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+
+  // ---- O = P V ----
+  float o[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
+#pragma unroll
+  for (int ks = 0; ks < kMaxKT / 2; ++ks) {
+    if (ks < nks) {
+      // V^T fragments via ldmatrix.trans: matrices (keys lo, d n0), (keys hi, d n0), (keys lo, d n0+8), (keys hi, d n0+8)
+      const int vr = ks * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+      const int dofs = (lane >> 4) * 8;
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {
+        uint32_t b0, b1, b2, b3;
+        ldmatrix_x4_trans(smem_u32(sV + vr * kPitch + dp * 16 + dofs), b0, b1, b2, b3);
+        mma_16816<E16>(o[2 * dp], pa[2 * ks][0], pa[2 * ks][1], pa[2 * ks + 1][0], pa[2 * ks + 1][1], b0, b1);
+        mma_16816<E16>(o[2 * dp + 1], pa[2 * ks][0], pa[2 * ks][1], pa[2 * ks + 1][0], pa[2 * ks + 1][1], b2, b3);
+      }
+    }
+  }
+
+  // ---- normalise and store the merged-head context rows ----
+  const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+  const int r0 = q0 + g, r1 = q0 + g + 8;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const int col = h * kHeadDim + nt * 8 + 2 * t4;
+    if (r0 < Sq) {
+      *reinterpret_cast<uint32_t*>(out + (int64_t(b) * Sq + r0) * ldo + col) = E16::pack(o[nt][0] * inv0, o[nt][1] * inv0);
+    }
+    if (r1 < Sq) {
+      *reinterpret_cast<uint32_t*>(out + (int64_t(b) * Sq + r1) * ldo + col) = E16::pack(o[nt][2] * inv1, o[nt][3] * inv1);
+    }
+  }
+}
+
+static size_t attention_smem_bytes(int Sq, int Sk) {
+  const int SqP = ((Sq + 15) / 16) * 16, SkP = ((Sk + 15) / 16) * 16;
+  return size_t(SqP + 2 * SkP) * kPitch * 2 + size_t(SkP) * 4;
+}
+
+template <class E16>
+static mmr_status launch_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                                   int64_t ldv, const int32_t* key_mask, void* out, int64_t ldo, int B, int Sq,
+                                   int Sk, int heads, cudaStream_t stream) {
+  using T = typename E16::T;
+  auto kern = attention_kernel<E16>;
+  static bool configured = false;
+  if (!configured) {
+    MMR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     int(attention_smem_bytes(kMaxSeq, kMaxSeq))));
+    configured = true;
+  }
+  const int nwarps = (Sq + 15) / 16;
+  dim3 grid(heads, B);
+  kern<<<grid, nwarps * 32, attention_smem_bytes(Sq, Sk), stream>>>(
+      static_cast<const T*>(q), ldq, static_cast<const T*>(k), ldk, static_cast<const T*>(v), ldv, key_mask,
+      static_cast<T*>(out), ldo, Sq, Sk);
+  MMR_CUDA_OK(cudaGetLastError());
+  return MMR_OK;
+}
+
+mmr_status attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                     const int32_t* key_mask, void* out16, int64_t ldo, int B, int Sq, int Sk, int heads,
+                     int dtype, cudaStream_t stream) {
+  MMR_TRY(require_sm100());
+  MMR_REQUIRE(q && k && v && out16, "mmr_attention: null pointer");
+  MMR_REQUIRE(B > 0 && heads > 0, "mmr_attention: B=%d heads=%d", B, heads);
+  MMR_REQUIRE(Sq > 0 && Sq <= kMaxSeq && Sk > 0 && Sk <= kMaxSeq, "mmr_attention: Sq=%d Sk=%d must be in [1,%d]",
+              Sq, Sk, kMaxSeq);
+  MMR_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 2 == 0,
+              "mmr_attention: row strides must keep 16-byte alignment of 64-wide head slices");
+  MMR_REQUIRE(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(out16) & 3) == 0,
+              "mmr_attention: q/k/v must be 16-byte aligned");
+  if (dtype == MMR_DT_BF16)
+    return launch_attention<BF16>(q, ldq, k, ldk, v, ldv, key_mask, out16, ldo, B, Sq, Sk, heads, stream);
+  if (dtype == MMR_DT_FP16)
+    return launch_attention<FP16>(q, ldq, k, ldk, v, ldv, key_mask, out16, ldo, B, Sq, Sk, heads, stream);
+  return fail(MMR_ERR_INVALID, "mmr_attention: bad dtype %d", dtype);
+}
+
+}  // namespace mmr
+
+extern "C" mmr_status mmr_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                                    int64_t ldv, const int32_t* key_mask, void* out16, int64_t ldo, int B, int Sq,
+                                    int Sk, int heads, int dtype, void* stream) {
+  return mmr::attention(q, ldq, k, ldk, v, ldv, key_mask, out16, ldo, B, Sq, Sk, heads, dtype,
+                        static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,58 @@
+// Error state and device gate behind the C ABI.
+#include "common.cuh"
+
+namespace mmr {
+
+char* last_error_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+
+mmr_status fail(mmr_status code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(last_error_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+mmr_status require_sm100() {
+  static thread_local int cached_dev = -1;
+  static thread_local mmr_status cached = MMR_ERR_ARCH;
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    return fail(MMR_ERR_ARCH, "no CUDA device available (%s); this library has no CPU fallback",
+                cudaGetErrorString(e));
+  }
+  if (dev == cached_dev) {
+    if (cached != MMR_OK) fail(cached, "device %d is not sm_100 (B200); no fallback path exists", dev);
+    return cached;
+  }
+  int major = 0, minor = 0;
+  MMR_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  MMR_CUDA_OK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  cached_dev = dev;
+  cached = (major == 10) ? MMR_OK : MMR_ERR_ARCH;
+  if (cached != MMR_OK) {
+    return fail(MMR_ERR_ARCH, "device %d is sm_%d%d, need sm_100 (B200); no fallback path exists", dev, major,
+                minor);
+  }
+  return MMR_OK;
+}
+
+}  // namespace mmr
+
+extern "C" const char* mmr_last_error(void) { return mmr::last_error_buf(); }
+extern "C" int mmr_abi_version(void) { return 1; }
+extern "C" mmr_status mmr_device_check(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) {
+    return mmr::fail(MMR_ERR_ARCH, "CUDA device %d not present; this library has no CPU fallback", device);
+  }
+  int major = 0, minor = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device);
+  if (major != 10) return mmr::fail(MMR_ERR_ARCH, "device %d is sm_%d%d, need sm_100 (B200)", device, major, minor);
+  return MMR_OK;
+}
