@@ -1,0 +1,16 @@
+"""CPU oracle — TEST INFRASTRUCTURE, NOT PRODUCT.
+
+fp32 PyTorch restatements of the reference's scoring hot path (zuokai/KDDCUP_2020_MultimodalitiesRecall_2nd_Place),
+each function citing the reference file:line it follows.  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this package, and only as the checker or the timed CPU baseline.
+The product (kddcup_2020_multimodalitiesrecall_2nd_place_b200) never imports it and has no CPU fallback.
+
+Pinning status
+  * ensemble (code/main.py) and nDCG@5: pinned by the reference's shipped files — tests/golden/ensemble_kat and
+    the nDCG known answer 0.7098 (kdd-report-final.pdf table 5) reproduced from shipped score files.
+  * LXMERT: pinned against the reference's OWN PyTorch code, imported from /root/reference in the dev container
+    (oracle/lxmert_ref.py); golden vectors generated from it are committed under tests/golden/ with the script.
+  * ImageBert zk / lds: TF-1.12 + Python 2 are not installable, and the reference ships no activations or weights:
+    PARITY UNPINNED for these two encoders beyond what they share with the pinned LXMERT blocks (attention,
+    post-LN block, LayerNorm, GELU, pooler).  The restatement follows SURVEY.md appendix A line by line.
+"""

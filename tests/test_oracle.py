@@ -1,0 +1,143 @@
+"""CPU tests pinning the oracle: golden vectors from the reference's shipped files / own LXMERT code."""
+import ast
+import hashlib
+import os
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+from kddcup_2020_multimodalitiesrecall_2nd_place_b200 import synth
+from kddcup_2020_multimodalitiesrecall_2nd_place_b200.config import LDS, LXMERT, ZK, ModelConfig
+from oracle import ensemble, imagebert, lxmert
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _scores_to_dict(q, p, s):
+    d = OrderedDict()
+    for qi, pi, si in zip(q.tolist(), p.tolist(), s.tolist()):
+        d.setdefault(str(qi), OrderedDict())[str(pi)] = si
+    return d
+
+
+def test_ensemble_known_answer():
+    """code/main.py:11-104 on the four shipped score files reproduces prediction_result/submission.csv exactly."""
+    g = np.load(os.path.join(GOLD, "ensemble_kat.npz"))
+    ds = [_scores_to_dict(g[t + "_q"], g[t + "_p"], g[t + "_s"]) for t in ("zk", "zk_s2f", "lds", "lxmert")]
+    rows, merged = ensemble.merge_and_select(*ds)
+    got = {int(q): [int(p) for p in ps] for q, ps in rows}
+    want = {int(r[0]): [int(x) for x in r[1:]] for r in g["submission"]}
+    assert len(rows) == 994 and len(got) == 994
+    assert got == want
+
+
+def test_ndcg_known_answer():
+    """evaluation.py nDCG@5 of the shipped ImageBertA valid scores = 0.7098 (report table 5)."""
+    g = np.load(os.path.join(GOLD, "ndcg_kat.npz"))
+    by_q = {}
+    for q, p, s in zip(g["q"].tolist(), g["p"].tolist(), g["s"].tolist()):
+        by_q.setdefault(q, []).append((p, s))
+    pred = {q: [p for p, _ in sorted(v, key=lambda t: t[1], reverse=True)] for q, v in by_q.items()}
+    ans = {int(q): {int(x) for x in row if x >= 0} for q, row in zip(g["ans_q"], g["ans"])}
+    val = ensemble.ndcg_at_k(pred, ans, 5)
+    assert abs(val - 0.7098) < 5e-5, val
+
+
+def _digest(w):
+    h = hashlib.sha256()
+    for k in sorted(w):
+        h.update(k.encode())
+        h.update(np.ascontiguousarray(w[k]).tobytes())
+    return h.hexdigest()
+
+
+@pytest.mark.parametrize("tag", ["small", "small_trained", "native", "cfg3shape"])
+def test_lxmert_restatement_matches_reference_code(tag):
+    """oracle/lxmert.py vs outputs of the reference's own KDDModel.forward (tools/make_golden.py)."""
+    g = np.load(os.path.join(GOLD, f"lxmert_ref_{tag}.npz"))
+    cfg = ModelConfig(**ast.literal_eval(str(g["cfg"])))
+    w = synth.make_weights(cfg, seed=int(g["seed"]), trained_like=bool(g["trained_like"]))
+    assert _digest(w) == str(g["weights_sha256"]), "synthetic weight generator drifted from the golden fixture"
+    inp = imagebert.to_torch(synth.make_inputs(cfg, int(g["batch"]), seed=int(g["seed"])))
+    out = lxmert.forward(imagebert.to_torch(w), inp, cfg.n_layers, cfg.n_r_layers, cfg.n_x_layers)
+    np.testing.assert_allclose(out["logit"].numpy(), g["logit"], atol=3e-5, rtol=1e-4)
+    np.testing.assert_allclose(out["probs"].numpy(), g["probs"], atol=1e-5)
+    np.testing.assert_allclose(out["x_norm"].numpy(), g["x_norm"], atol=1e-5)
+
+
+def test_zk_label_conv_same_padding_matches_conv2d():
+    """Quirk 1+2: slim.conv2d [1,8] SAME = pad 3 left / 4 right, bias, ReLU, then mean."""
+    cfg = ModelConfig(ZK, n_layers=1, lq=6, nbox=3, vocab=50)
+    w = imagebert.to_torch(synth.make_weights(cfg, seed=5, trained_like=True))
+    ids = torch.randint(0, 50, (2, 3, 8))
+    got = imagebert.zk_label_term(ids, w)
+    lab = w["bert/embeddings/word_embeddings"][ids]                      # [B,R,8,H]
+    x = lab.permute(0, 3, 1, 2)                                          # NCHW: [B,H,R,8]
+    k = w["kdd_conv1/weights"].permute(3, 2, 0, 1)                       # HWIO -> OIHW
+    y = torch.nn.functional.conv2d(torch.nn.functional.pad(x, (3, 4)), k, w["kdd_conv1/biases"])
+    want = torch.relu(y).mean(dim=3).permute(0, 2, 1)
+    np.testing.assert_allclose(got.numpy(), want.numpy(), atol=2e-5)
+
+
+def test_lds_reshape4d_quirk():
+    """Quirk 6: output dim j mixes 8 consecutive hidden dims of token floor(8j/H) (pixelmodel.py:489-498)."""
+    cfg = ModelConfig(LDS, n_layers=1, lq=6, nbox=2, vocab=50)
+    w = imagebert.to_torch(synth.make_weights(cfg, seed=6))
+    ids = torch.randint(0, 50, (2, 2, 8))
+    got = imagebert.lds_label_term(ids, w)
+    E, wl = w["bert/embeddings/word_embeddings"], w["bert/embeddings/word_embeddings_labelembedding"][:, 0]
+    H = E.shape[1]
+    want = torch.zeros(2, 2, H)
+    for b in range(2):
+        for r in range(2):
+            for j in range(H):
+                t, h0 = (8 * j) // H, (8 * j) % H
+                want[b, r, j] = (E[ids[b, r, t], h0:h0 + 8] * wl).sum()
+    np.testing.assert_allclose(got.numpy(), want.numpy(), atol=1e-6)
+
+
+@pytest.mark.parametrize("kind", [ZK, LDS])
+def test_imagebert_oracle_properties(kind):
+    """Padding invariance (zk: masked keys do not change the score; lds has NO mask so they do), batch
+    permutation invariance, probabilities sum to one."""
+    cfg = ModelConfig(kind, n_layers=2, lq=20, nbox=8, vocab=500)
+    w = imagebert.to_torch(synth.make_weights(cfg, seed=11, trained_like=True))
+    inp = imagebert.to_torch(synth.make_inputs(cfg, 4, seed=11))
+    fwd = imagebert.zk_forward if kind == ZK else imagebert.lds_forward
+    base = fwd(w, inp, cfg.n_layers)["probs"]
+    assert torch.allclose(base.sum(1), torch.ones(4), atol=1e-6)
+    perm = torch.tensor([2, 0, 3, 1])
+    inp_p = {k: v[perm] for k, v in inp.items()}
+    assert torch.allclose(fwd(w, inp_p, cfg.n_layers)["probs"], base[perm], atol=1e-5)
+    # perturb the features of padded boxes
+    inp2 = dict(inp)
+    f2 = inp["feats"].clone()
+    nb = inp["num_boxes"]
+    changed = False
+    for b in range(4):
+        if nb[b] < cfg.nbox:
+            f2[b, nb[b]:] += 1.0
+            changed = True
+    assert changed
+    inp2["feats"] = f2
+    out2 = fwd(w, inp2, cfg.n_layers)["probs"]
+    if kind == ZK:
+        # padded boxes are masked as KEYS, and [CLS] (query position 0) never reads them
+        assert torch.allclose(out2, base, atol=1e-5)
+    else:
+        assert not torch.allclose(out2, base, atol=1e-7)
+
+
+def test_zk_margin_uses_fed_label():
+    """Quirk 5: the AM-softmax margin is applied to the FED label's cosine when it exceeds 0.35."""
+    w = {"cls/seq_relationship/am_kernel": torch.tensor([[1.0, 0.0], [0.0, 1.0]] + [[0.0, 0.0]] * 766)}
+    pooled = torch.zeros(2, 768)
+    pooled[0, 1] = 1.0          # cos = [0, 1] -> label-1 cosine 1 > 0.35 -> 0.65
+    pooled[1, 0], pooled[1, 1] = 0.95, 0.3122499  # label-1 cosine 0.31 <= 0.35 -> untouched
+    p = imagebert.amsoftmax_probs(pooled, torch.tensor([1, 1]), w)
+    want0 = torch.softmax(torch.tensor([0.0, 30 * 0.65]), 0)
+    n = (0.95 ** 2 + 0.3122499 ** 2) ** 0.5
+    want1 = torch.softmax(torch.tensor([30 * 0.95 / n, 30 * 0.3122499 / n]), 0)
+    assert torch.allclose(p[0], want0, atol=1e-6) and torch.allclose(p[1], want1, atol=1e-5)
