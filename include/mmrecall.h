@@ -152,11 +152,22 @@ void mmr_destroy(mmr_handle* h);
 mmr_status mmr_forward(mmr_handle* h, const mmr_inputs* in, int B, float* probs_out, float* pooled_out,
                        void* stream);
 
-/* Debug / parity taps: copies of internal activations after the last forward (dev fp32).
- * which: 0 = embedding output [B*S, hidden]; 1 = final encoder layer output (lang stream for LXMERT). */
+/* Debug / parity taps (BertModel.get_embedding_output / get_sequence_output, pixelbert.py:279-309): copies of
+ * internal activations after the last forward (dev fp32, rows = pairs x tokens; LXMERT: all language rows, then all
+ * visual rows).  which: 0 = embedding output, only kept when mmr_set_debug_taps(h, 1) was called before the forward
+ * (one extra device copy per forward); 1 = final encoder layer output. */
+mmr_status mmr_set_debug_taps(mmr_handle* h, int enable);
 mmr_status mmr_get_activation(mmr_handle* h, int which, float* dst, int64_t n_floats, void* stream);
 
-/* Number of kernels one mmr_forward launches for batch B (for bench.py's gpu_launches claim). */
+/* Per-launch device timing inside a forward, for bench.py's roofline line: with profiling enabled every kernel
+ * launch of mmr_forward is followed by a cudaEventRecord on the forward's stream.  mmr_get_profile waits for the
+ * last forward and returns the number of launches n (<= cap), filling kinds[i] (0 tcgen05 GEMM, 1 attention,
+ * 2 LayerNorm, 3 embedding / head row kernels), ms[i] (device time from the previous event) and flops[i]
+ * (algorithmic FLOPs of that launch, multiply-add = 2); -1 on a CUDA error. */
+mmr_status mmr_set_profiling(mmr_handle* h, int enable);
+int mmr_get_profile(mmr_handle* h, int cap, int32_t* kinds, float* ms, double* flops);
+
+/* Number of kernels the last mmr_forward launched (for bench.py's gpu_launches claim). */
 int mmr_launches_per_forward(const mmr_handle* h);
 
 #ifdef __cplusplus

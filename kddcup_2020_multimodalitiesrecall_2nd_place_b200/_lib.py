@@ -16,7 +16,8 @@ MODEL_ZK, MODEL_LDS, MODEL_LXMERT = range(3)
 EXPORTS = [
     "mmr_last_error", "mmr_abi_version", "mmr_device_check",
     "mmr_gemm", "mmr_layernorm", "mmr_attention", "mmr_cast16",
-    "mmr_create", "mmr_destroy", "mmr_forward", "mmr_get_activation", "mmr_launches_per_forward",
+    "mmr_create", "mmr_destroy", "mmr_forward", "mmr_set_debug_taps", "mmr_get_activation",
+    "mmr_launches_per_forward", "mmr_set_profiling", "mmr_get_profile",
 ]
 
 
@@ -65,13 +66,16 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.mmr_layernorm.argtypes = [vp, i64, vp, vp, f32, i32, i32, vp, i64, vp, i64, f32, i32, i32, vp]
     lib.mmr_attention.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, i64, i32, i32, i32, i32, i32, vp]
     lib.mmr_cast16.argtypes = [vp, vp, i64, i32, vp]
-    if hasattr(lib, "mmr_create"):
+    if True:
         lib.mmr_create.argtypes = [C.POINTER(MmrConfig), C.POINTER(MmrTensor), i32, i32, C.POINTER(vp)]
         lib.mmr_destroy.argtypes = [vp]
         lib.mmr_destroy.restype = None
         lib.mmr_forward.argtypes = [vp, C.POINTER(MmrInputs), i32, vp, vp, vp]
+        lib.mmr_set_debug_taps.argtypes = [vp, i32]
         lib.mmr_get_activation.argtypes = [vp, i32, vp, i64, vp]
         lib.mmr_launches_per_forward.argtypes = [vp]
+        lib.mmr_set_profiling.argtypes = [vp, i32]
+        lib.mmr_get_profile.argtypes = [vp, i32, vp, vp, vp]
     _lib = lib
     return lib
 

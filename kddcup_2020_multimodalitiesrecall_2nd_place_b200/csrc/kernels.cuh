@@ -1,0 +1,42 @@
+// Internal (C++) launcher declarations shared by the model driver; the C ABI wraps a subset of these.
+#pragma once
+#include "common.cuh"
+
+namespace mmr {
+
+mmr_status gemm(const void* A16, int64_t lda, const void* W16, int64_t ldw, int M, int N, int K,
+                const float* bias, const float* residual, int64_t ldr, void* out16, int64_t ldo16,
+                float* out32, int64_t ldo32, int act, int dtype, cudaStream_t stream);
+mmr_status layernorm(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, int M, int H,
+                     void* out16, int64_t ldo16, float* out32, int64_t ldo32, float scale, int accumulate,
+                     int dtype, cudaStream_t stream);
+mmr_status attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                     const int32_t* key_mask, void* out16, int64_t ldo, int B, int Sq, int Sk, int heads,
+                     int dtype, cudaStream_t stream);
+mmr_status cast16(const float* x, void* out16, int64_t n, int dtype, cudaStream_t stream);
+
+mmr_status zk_region_sum(const float* feat32, const float* boxes5, const int32_t* label_ids, const float* tables,
+                         int vocab, const float* bc1, const float* Wb, const float* bb, void* out16, int rows,
+                         int dtype, cudaStream_t st);
+mmr_status zk_embed(const int32_t* query_ids, const int32_t* segment_ids, const float* region32,
+                    const int32_t* len_query, const int32_t* num_boxes, const float* E, const float* T,
+                    const float* P, const float* gamma, const float* beta, int Lq, int R, int B, void* x16,
+                    float* x32, int32_t* key_mask, int dtype, cudaStream_t st);
+mmr_status lds_embed(const int32_t* query_ids, const int32_t* segment_ids, const int32_t* label_ids,
+                     const float* region32, const float* E, const float* T, const float* P, const float* gamma,
+                     const float* beta, const float* wl, int Lq, int R, int B, void* x16, float* x32, int dtype,
+                     cudaStream_t st);
+mmr_status lx_lang_embed(const int32_t* query_ids, const float* E, const float* T, const float* P,
+                         const float* gamma, const float* beta, int Lq, int B, void* x16, float* x32, int dtype,
+                         cudaStream_t st);
+mmr_status lx_label_z(const int32_t* label_ids, const float* E, const float* T, const float* P,
+                      const float* gamma, const float* beta, const float* wconv, const float* bconv, int rows,
+                      void* z16, int dtype, cudaStream_t st);
+mmr_status lx_box_ln(const float* boxes4, const float* Wb, const float* bb, const float* gamma, const float* beta,
+                     float scale, int rows, float* acc32, cudaStream_t st);
+mmr_status zk_head(const float* pooled, const float* wn, const int32_t* labels, int B, float* probs,
+                   cudaStream_t st);
+mmr_status linear_head(const float* x, int width, const float* ln_gamma, const float* ln_beta, const float* W,
+                       const float* bias, int B, float* probs, cudaStream_t st);
+
+}  // namespace mmr

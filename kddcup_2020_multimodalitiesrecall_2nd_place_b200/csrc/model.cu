@@ -1,0 +1,819 @@
+// Model driver behind mmr_create / mmr_forward: packs reference-named fp32 weights into device-resident 16-bit
+// [out,in] matrices (+ fp32 biases / LayerNorm / embedding tables) and sequences the kernels of this directory for
+// the three scorers.  Replaces, end to end on the device:
+//   zk     model_triple.model_attention_channel_e            (imagebert_zk/model_triple.py:162-214)
+//   lds    pixelmodel.BertModel + get_next_sentence_output   (imagebert_lds/src/pixelmodel.py:145-270,
+//                                                             run_pretraining_predict_score.py:288-394, 479-501)
+//   lxmert KDDModel.forward                                  (lxmert/src/tasks/kdd_model.py:183-214,
+//                                                             lxrt/modeling.py:872-927)
+// Layout in HBM: one arena for weights, one for the per-forward workspace (sized for max_batch at create time, no
+// allocation or synchronisation inside mmr_forward).  The residual stream lives in ONE fp32 buffer x32 [M,768]
+// that GEMM epilogues (+bias +residual) and the LayerNorm kernel update in place, with its 16-bit mirror x16 as
+// the next GEMM's TMA operand.  LXMERT's two streams share these buffers: rows [0, B*Lq) are the language
+// stream, rows [B*Lq, B*(Lq+R)) the visual stream, so the weight-shared cross-attention block (modeling.py:462-463)
+// runs its QKV and output projections as single GEMMs over all rows.
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace mmr {
+
+// ------------------------------------------------------------------------------------------ pack kernels
+// dst16[r, c] = src32[r, c] (transpose = 0) or src32[c, r] (transpose = 1; src is [cols, rows]).
+template <class E16>
+__global__ void pack16_kernel(const float* __restrict__ src, typename E16::T* __restrict__ dst, int rows, int cols,
+                              int transpose) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  if (!transpose) {
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int r = r0 + i, c = c0 + threadIdx.x;
+      if (r < rows && c < cols) {
+        uint32_t pk = E16::pack(src[int64_t(r) * cols + c], 0.f);
+        reinterpret_cast<uint16_t*>(dst)[int64_t(r) * cols + c] = uint16_t(pk & 0xffffu);
+      }
+    }
+    return;
+  }
+  // src is [cols, rows] row-major; read coalesced along its rows-dimension, write coalesced along cols.
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int sc = c0 + i, sr = r0 + threadIdx.x;  // src element (sc, sr)
+    tile[i][threadIdx.x] = (sc < cols && sr < rows) ? src[int64_t(sc) * rows + sr] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) {
+      uint32_t pk = E16::pack(tile[threadIdx.x][i], 0.f);
+      reinterpret_cast<uint16_t*>(dst)[int64_t(r) * cols + c] = uint16_t(pk & 0xffffu);
+    }
+  }
+}
+
+// hi = round16(x), lo = round16(x - hi): two-term split used once at create time for the zk label tables.
+template <class E16>
+__global__ void split16_kernel(const float* __restrict__ x, typename E16::T* __restrict__ hi,
+                               typename E16::T* __restrict__ lo, int64_t n) {
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) {
+    const float v = x[i];
+    const uint32_t ph = E16::pack(v, 0.f);
+    const float h = E16::unpack(ph).x;
+    const uint32_t pl = E16::pack(v - h, 0.f);
+    reinterpret_cast<uint16_t*>(hi)[i] = uint16_t(ph & 0xffffu);
+    reinterpret_cast<uint16_t*>(lo)[i] = uint16_t(pl & 0xffffu);
+  }
+}
+
+static mmr_status pack16(const float* src_dev, void* dst16, int rows, int cols, bool transpose, int dtype,
+                         cudaStream_t st) {
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  if (dtype == MMR_DT_BF16)
+    pack16_kernel<BF16><<<grid, block, 0, st>>>(src_dev, static_cast<BF16::T*>(dst16), rows, cols, transpose);
+  else
+    pack16_kernel<FP16><<<grid, block, 0, st>>>(src_dev, static_cast<FP16::T*>(dst16), rows, cols, transpose);
+  MMR_CUDA_OK(cudaGetLastError());
+  return MMR_OK;
+}
+
+static mmr_status split16(const float* x, void* hi, void* lo, int64_t n, int dtype, cudaStream_t st) {
+  const int grid = int(std::min<int64_t>((n + 255) / 256, 148 * 8));
+  if (dtype == MMR_DT_BF16)
+    split16_kernel<BF16><<<grid, 256, 0, st>>>(x, static_cast<BF16::T*>(hi), static_cast<BF16::T*>(lo), n);
+  else
+    split16_kernel<FP16><<<grid, 256, 0, st>>>(x, static_cast<FP16::T*>(hi), static_cast<FP16::T*>(lo), n);
+  MMR_CUDA_OK(cudaGetLastError());
+  return MMR_OK;
+}
+
+// ------------------------------------------------------------------------------------------ handle
+struct Linear {
+  void* w16 = nullptr;   // [n, k] 16-bit
+  float* bias = nullptr; // [n] or null
+  int n = 0, k = 0;
+};
+struct LNp {
+  float* gamma = nullptr;
+  float* beta = nullptr;
+};
+struct AttBlock {  // attention + output projection + LayerNorm (pixelbert.py:658-852, 960-966; modeling.py:369-391)
+  Linear qkv, out;
+  LNp ln;
+};
+struct FfnBlock {  // pixelbert.py:969-983; modeling.py:394-420
+  Linear in, out;
+  LNp ln;
+};
+struct Layer {
+  AttBlock att;
+  FfnBlock ffn;
+};
+struct XLayer {  // modeling.py:444-493
+  AttBlock cross, lang_self, visn_self;
+  FfnBlock lang_ffn, visn_ffn;
+};
+
+struct Arena {
+  uint8_t* base = nullptr;
+  size_t cap = 0, used = 0;
+  void* take(size_t bytes) {
+    const size_t off = (used + 255) & ~size_t(255);
+    if (off + bytes > cap) return nullptr;
+    used = off + bytes;
+    return base + off;
+  }
+};
+
+}  // namespace mmr
+
+struct mmr_handle {
+  mmr_config cfg{};
+  int device = 0;
+  int act = MMR_ACT_GELU_TANH;
+  mmr::Arena weights, work;
+  // embeddings (fp32)
+  float *E = nullptr, *T = nullptr, *P = nullptr;
+  mmr::LNp emb_ln;
+  std::vector<mmr::Layer> layers, r_layers;
+  std::vector<mmr::XLayer> x_layers;
+  mmr::Linear pooler;
+  // zk
+  mmr::Linear conv2, featureemb;
+  float *tables = nullptr, *bc1 = nullptr, *Wb = nullptr, *bb = nullptr, *am_wn = nullptr;
+  // lds
+  mmr::Linear lds_feat;
+  float *wl = nullptr, *cls_w = nullptr, *cls_b = nullptr;
+  // lxmert
+  mmr::Linear visn_fc, label_fc, logit0;
+  mmr::LNp visn_ln, box_ln, label_ln, logit_ln;
+  float *box_w = nullptr, *box_b = nullptr, *wconv = nullptr, *bconv = nullptr, *logit3_w = nullptr,
+        *logit3_b = nullptr;
+  // workspace
+  void *f16 = nullptr, *t16 = nullptr, *x16 = nullptr, *qkv16 = nullptr, *ctx16 = nullptr, *h16 = nullptr,
+       *pooled16 = nullptr;
+  float *tmp32 = nullptr, *x32 = nullptr, *pooled32 = nullptr, *head32 = nullptr, *emb_tap = nullptr;
+  int32_t* key_mask = nullptr;
+  int64_t rows_max = 0;   // encoder rows at max_batch
+  int last_B = 0;
+  int launches = 0;
+  int keep_taps = 0;
+  // per-launch event profiling (mmr_set_profiling / mmr_get_profile)
+  int prof_on = 0, prof_n = 0;
+  std::vector<cudaEvent_t> prof_ev;
+  std::vector<int> prof_kind;
+  std::vector<double> prof_flops;
+};
+
+namespace mmr {
+
+using TensorMap = std::map<std::string, const mmr_tensor*>;
+
+static int64_t numel(const mmr_tensor* t) {
+  int64_t n = 1;
+  for (int i = 0; i < t->ndim; ++i) n *= t->dims[i];
+  return n;
+}
+
+struct Packer {
+  mmr_handle* h;
+  const TensorMap& tm;
+  float* staging;       // device fp32 staging for matrices
+  size_t staging_floats;
+  cudaStream_t st;
+
+  mmr_status find(const std::string& name, int64_t want_numel, const mmr_tensor** out) const {
+    auto it = tm.find(name);
+    if (it == tm.end()) return fail(MMR_ERR_WEIGHTS, "weight '%s' is missing", name.c_str());
+    if (numel(it->second) != want_numel)
+      return fail(MMR_ERR_WEIGHTS, "weight '%s' has %lld elements, expected %lld", name.c_str(),
+                  (long long)numel(it->second), (long long)want_numel);
+    if (it->second->data == nullptr) return fail(MMR_ERR_WEIGHTS, "weight '%s' has a null data pointer", name.c_str());
+    *out = it->second;
+    return MMR_OK;
+  }
+  // fp32 vector / table copied verbatim
+  mmr_status f32(const std::string& name, int64_t n, float** out) {
+    const mmr_tensor* t;
+    MMR_TRY(find(name, n, &t));
+    float* d = static_cast<float*>(h->weights.take(size_t(n) * 4));
+    if (!d) return fail(MMR_ERR_NOMEM, "weight arena exhausted at '%s'", name.c_str());
+    MMR_CUDA_OK(cudaMemcpyAsync(d, t->data, size_t(n) * 4, cudaMemcpyHostToDevice, st));
+    *out = d;
+    return MMR_OK;
+  }
+  // 16-bit [n,k] matrix into dst16 (row offset already applied).  tf_layout: source is [k,n] ("kernel").
+  mmr_status mat_into(const std::string& name, int n, int k, bool tf_layout, void* dst16) {
+    const mmr_tensor* t;
+    MMR_TRY(find(name, int64_t(n) * k, &t));
+    if (size_t(n) * k > staging_floats) return fail(MMR_ERR_INVALID, "staging too small for '%s'", name.c_str());
+    MMR_CUDA_OK(cudaMemcpyAsync(staging, t->data, size_t(n) * k * 4, cudaMemcpyHostToDevice, st));
+    MMR_TRY(pack16(staging, dst16, n, k, tf_layout, h->cfg.dtype, st));
+    // staging is reused by the next call: the pageable H2D copy above is synchronous w.r.t. the host buffer but
+    // the device-side order on `st` already serialises copy -> pack -> next copy.
+    return MMR_OK;
+  }
+  mmr_status linear(const std::string& wname, const std::string& bname, int n, int k, bool tf_layout, Linear* L) {
+    L->n = n;
+    L->k = k;
+    L->w16 = h->weights.take(size_t(n) * k * 2);
+    if (!L->w16) return fail(MMR_ERR_NOMEM, "weight arena exhausted at '%s'", wname.c_str());
+    MMR_TRY(mat_into(wname, n, k, tf_layout, L->w16));
+    if (!bname.empty()) MMR_TRY(f32(bname, n, &L->bias));
+    return MMR_OK;
+  }
+  // fused [3H, H] QKV projection from three reference tensors
+  mmr_status qkv(const std::string& prefix, const char* wsuffix, const char* bsuffix, bool tf_layout, Linear* L) {
+    const int H = h->cfg.hidden;
+    L->n = 3 * H;
+    L->k = H;
+    L->w16 = h->weights.take(size_t(3) * H * H * 2);
+    L->bias = static_cast<float*>(h->weights.take(size_t(3) * H * 4));
+    if (!L->w16 || !L->bias) return fail(MMR_ERR_NOMEM, "weight arena exhausted at '%s'", prefix.c_str());
+    const char* names[3] = {"query", "key", "value"};
+    for (int i = 0; i < 3; ++i) {
+      MMR_TRY(mat_into(prefix + names[i] + wsuffix, H, H, tf_layout,
+                       static_cast<uint8_t*>(L->w16) + size_t(i) * H * H * 2));
+      const mmr_tensor* t;
+      MMR_TRY(find(prefix + names[i] + bsuffix, H, &t));
+      MMR_CUDA_OK(cudaMemcpyAsync(L->bias + i * H, t->data, size_t(H) * 4, cudaMemcpyHostToDevice, st));
+    }
+    return MMR_OK;
+  }
+  mmr_status ln(const std::string& gname, const std::string& bname, int n, LNp* p) {
+    MMR_TRY(f32(gname, n, &p->gamma));
+    MMR_TRY(f32(bname, n, &p->beta));
+    return MMR_OK;
+  }
+};
+
+static mmr_status pack_tf_layer(Packer& pk, const std::string& p, Layer* L) {
+  const int H = pk.h->cfg.hidden, I = pk.h->cfg.intermediate;
+  MMR_TRY(pk.qkv(p + "attention/self/", "/kernel", "/bias", true, &L->att.qkv));
+  MMR_TRY(pk.linear(p + "attention/output/dense/kernel", p + "attention/output/dense/bias", H, H, true, &L->att.out));
+  MMR_TRY(pk.ln(p + "attention/output/LayerNorm/gamma", p + "attention/output/LayerNorm/beta", H, &L->att.ln));
+  MMR_TRY(pk.linear(p + "intermediate/dense/kernel", p + "intermediate/dense/bias", I, H, true, &L->ffn.in));
+  MMR_TRY(pk.linear(p + "output/dense/kernel", p + "output/dense/bias", H, I, true, &L->ffn.out));
+  MMR_TRY(pk.ln(p + "output/LayerNorm/gamma", p + "output/LayerNorm/beta", H, &L->ffn.ln));
+  return MMR_OK;
+}
+
+static mmr_status pack_torch_att(Packer& pk, const std::string& att, const std::string& out, AttBlock* A) {
+  const int H = pk.h->cfg.hidden;
+  MMR_TRY(pk.qkv(att, ".weight", ".bias", false, &A->qkv));
+  MMR_TRY(pk.linear(out + "dense.weight", out + "dense.bias", H, H, false, &A->out));
+  MMR_TRY(pk.ln(out + "LayerNorm.weight", out + "LayerNorm.bias", H, &A->ln));
+  return MMR_OK;
+}
+static mmr_status pack_torch_ffn(Packer& pk, const std::string& in, const std::string& out, FfnBlock* F) {
+  const int H = pk.h->cfg.hidden, I = pk.h->cfg.intermediate;
+  MMR_TRY(pk.linear(in + "dense.weight", in + "dense.bias", I, H, false, &F->in));
+  MMR_TRY(pk.linear(out + "dense.weight", out + "dense.bias", H, I, false, &F->out));
+  MMR_TRY(pk.ln(out + "LayerNorm.weight", out + "LayerNorm.bias", H, &F->ln));
+  return MMR_OK;
+}
+
+static size_t weight_arena_bytes(const mmr_config& c) {
+  const size_t H = c.hidden, I = c.intermediate, V = c.vocab;
+  const size_t att = 4 * H * H * 2 + 4 * H * 4 + 2 * H * 4 + 8 * 256;
+  const size_t ffn = 2 * H * I * 2 + (H + I) * 4 + 2 * H * 4 + 8 * 256;
+  size_t n = (V + c.max_pos + c.type_vocab + 2) * H * 4 + 16 * 256;
+  n += size_t(c.n_layers + c.n_r_layers) * (att + ffn);
+  n += size_t(c.n_x_layers) * (3 * att + 2 * ffn);
+  n += H * H * 2 + H * 4;  // pooler
+  n += size_t(c.feat_dim) * H * 2 + 2 * H * H * 2 + 64 * H * 4 + (1 << 20);  // projections, heads, small stuff
+  if (c.model_kind == MMR_MODEL_IMAGEBERT_ZK) n += size_t(c.label_len) * V * H * 4;  // label tables
+  return n;
+}
+
+__global__ void transpose32_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
+  // dst [cols, rows] = src [rows, cols]^T
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? src[int64_t(r) * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) dst[int64_t(c) * rows + r] = tile[threadIdx.x][i];
+  }
+}
+static mmr_status transpose32(const float* src, float* dst, int rows, int cols, cudaStream_t st) {
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  transpose32_kernel<<<grid, block, 0, st>>>(src, dst, rows, cols);
+  MMR_CUDA_OK(cudaGetLastError());
+  return MMR_OK;
+}
+
+// T_k = E . Wc1[k] in near-fp32 precision through three 16-bit GEMMs on split operands (create time only).
+static mmr_status build_zk_tables(Packer& pk) {
+  mmr_handle* h = pk.h;
+  const int H = h->cfg.hidden, V = h->cfg.vocab, Tn = h->cfg.label_len;
+  const int dt = h->cfg.dtype;
+  const mmr_tensor* wt;
+  MMR_TRY(pk.find("kdd_conv1/weights", int64_t(Tn) * H * H, &wt));
+  h->tables = static_cast<float*>(h->weights.take(size_t(Tn) * V * H * 4));
+  if (!h->tables) return fail(MMR_ERR_NOMEM, "weight arena exhausted at the zk label tables");
+  // scratch: E hi/lo [V,H], W hi/lo [H,H] 16-bit, W^T fp32 [H,H]
+  void *Eh, *El, *Wh, *Wl;
+  float* WT;
+  MMR_CUDA_OK(cudaMalloc(&Eh, size_t(V) * H * 2));
+  MMR_CUDA_OK(cudaMalloc(&El, size_t(V) * H * 2));
+  MMR_CUDA_OK(cudaMalloc(&Wh, size_t(H) * H * 2));
+  MMR_CUDA_OK(cudaMalloc(&Wl, size_t(H) * H * 2));
+  MMR_CUDA_OK(cudaMalloc(&WT, size_t(H) * H * 4));
+  mmr_status rc = split16(h->E, Eh, El, int64_t(V) * H, dt, pk.st);
+  for (int k = 0; k < Tn && rc == MMR_OK; ++k) {
+    // Wc1[0,k] is [Hin,Hout]; the GEMM wants [Hout,Hin].  Transpose in fp32 so the split sees unrounded values.
+    if (cudaMemcpyAsync(pk.staging, wt->data + size_t(k) * H * H, size_t(H) * H * 4, cudaMemcpyHostToDevice,
+                        pk.st) != cudaSuccess) {
+      rc = fail(MMR_ERR_CUDA, "upload of kdd_conv1 tap %d failed", k);
+      break;
+    }
+    rc = transpose32(pk.staging, WT, H, H, pk.st);
+    if (rc != MMR_OK) break;
+    rc = split16(WT, Wh, Wl, int64_t(H) * H, dt, pk.st);
+    if (rc != MMR_OK) break;
+    float* out = h->tables + size_t(k) * V * H;
+    rc = gemm(Eh, H, Wh, H, V, H, H, nullptr, nullptr, 0, nullptr, 0, out, H, MMR_ACT_NONE, dt, pk.st);
+    if (rc != MMR_OK) break;
+    rc = gemm(Eh, H, Wl, H, V, H, H, nullptr, out, H, nullptr, 0, out, H, MMR_ACT_NONE, dt, pk.st);
+    if (rc != MMR_OK) break;
+    rc = gemm(El, H, Wh, H, V, H, H, nullptr, out, H, nullptr, 0, out, H, MMR_ACT_NONE, dt, pk.st);
+  }
+  cudaStreamSynchronize(pk.st);
+  cudaFree(Eh); cudaFree(El); cudaFree(Wh); cudaFree(Wl); cudaFree(WT);
+  return rc;
+}
+
+static mmr_status pack_weights(mmr_handle* h, const TensorMap& tm, cudaStream_t st) {
+  const mmr_config& c = h->cfg;
+  const int H = c.hidden, F = c.feat_dim;
+  const size_t staging_floats = std::max<size_t>(size_t(H) * c.intermediate, size_t(F) * H);
+  float* staging = nullptr;
+  MMR_CUDA_OK(cudaMalloc(&staging, staging_floats * 4));
+  Packer pk{h, tm, staging, staging_floats, st};
+  mmr_status rc = MMR_OK;
+#define PK(expr)                     \
+  do {                               \
+    rc = (expr);                     \
+    if (rc != MMR_OK) goto done;     \
+  } while (0)
+
+  if (c.model_kind == MMR_MODEL_IMAGEBERT_ZK || c.model_kind == MMR_MODEL_IMAGEBERT_LDS) {
+    h->act = MMR_ACT_GELU_TANH;
+    PK(pk.f32("bert/embeddings/word_embeddings", int64_t(c.vocab) * H, &h->E));
+    PK(pk.f32("bert/embeddings/token_type_embeddings", int64_t(c.type_vocab) * H, &h->T));
+    PK(pk.f32("bert/embeddings/position_embeddings", int64_t(c.max_pos) * H, &h->P));
+    PK(pk.ln("bert/embeddings/LayerNorm/gamma", "bert/embeddings/LayerNorm/beta", H, &h->emb_ln));
+    h->layers.resize(c.n_layers);
+    for (int i = 0; i < c.n_layers; ++i)
+      PK(pack_tf_layer(pk, "bert/encoder/layer_" + std::to_string(i) + "/", &h->layers[i]));
+    PK(pk.linear("bert/pooler/dense/kernel", "bert/pooler/dense/bias", H, H, true, &h->pooler));
+    if (c.model_kind == MMR_MODEL_IMAGEBERT_ZK) {
+      PK(pk.linear("kdd_conv2/weights", "kdd_conv2/biases", H, F, true, &h->conv2));
+      PK(pk.linear("kdd_featureemb/fully_connected/weights", "kdd_featureemb/fully_connected/biases", H, H, true,
+                   &h->featureemb));
+      PK(pk.f32("kdd_conv1/biases", H, &h->bc1));
+      PK(pk.f32("kdd_dense1/weights", int64_t(5) * H, &h->Wb));
+      PK(pk.f32("kdd_dense1/biases", H, &h->bb));
+      {
+        // column-normalised AM-softmax kernel, stored [2,768] (model_triple.py:64: l2_normalize(kernel, 0, 1e-10))
+        const mmr_tensor* t;
+        PK(pk.find("cls/seq_relationship/am_kernel", int64_t(H) * 2, &t));
+        std::vector<float> wn(size_t(2) * H);
+        for (int j = 0; j < 2; ++j) {
+          float ss = 0.f;
+          for (int i = 0; i < H; ++i) ss += t->data[i * 2 + j] * t->data[i * 2 + j];
+          const float inv = 1.0f / std::sqrt(std::max(ss, 1e-10f));
+          for (int i = 0; i < H; ++i) wn[size_t(j) * H + i] = t->data[i * 2 + j] * inv;
+        }
+        h->am_wn = static_cast<float*>(h->weights.take(wn.size() * 4));
+        if (!h->am_wn) { rc = fail(MMR_ERR_NOMEM, "weight arena exhausted at am_kernel"); goto done; }
+        if (cudaMemcpyAsync(h->am_wn, wn.data(), wn.size() * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) {
+          rc = fail(MMR_ERR_CUDA, "upload of am_kernel failed");
+          goto done;
+        }
+      }
+      PK(build_zk_tables(pk));
+    } else {
+      PK(pk.linear("featureemb/fully_connected/weights", "featureemb/fully_connected/biases", H, F, true,
+                   &h->lds_feat));
+      PK(pk.f32("bert/embeddings/word_embeddings_labelembedding", c.label_len, &h->wl));
+      PK(pk.f32("cls/seq_relationship/output_weights", int64_t(2) * H, &h->cls_w));
+      PK(pk.f32("cls/seq_relationship/output_bias", 2, &h->cls_b));
+    }
+  } else {
+    h->act = MMR_ACT_GELU_ERF;
+    const std::string b = "lxrt_encoder.model.bert.";
+    PK(pk.f32(b + "embeddings.word_embeddings.weight", int64_t(c.vocab) * H, &h->E));
+    PK(pk.f32(b + "embeddings.token_type_embeddings.weight", int64_t(c.type_vocab) * H, &h->T));
+    PK(pk.f32(b + "embeddings.position_embeddings.weight", int64_t(c.max_pos) * H, &h->P));
+    PK(pk.ln(b + "embeddings.LayerNorm.weight", b + "embeddings.LayerNorm.bias", H, &h->emb_ln));
+    const std::string v = b + "encoder.visn_fc.";
+    PK(pk.linear(v + "visn_fc.weight", v + "visn_fc.bias", H, F, false, &h->visn_fc));
+    PK(pk.ln(v + "visn_layer_norm.weight", v + "visn_layer_norm.bias", H, &h->visn_ln));
+    PK(pk.f32(v + "box_fc.weight", int64_t(H) * 4, &h->box_w));
+    PK(pk.f32(v + "box_fc.bias", H, &h->box_b));
+    PK(pk.ln(v + "box_layer_norm.weight", v + "box_layer_norm.bias", H, &h->box_ln));
+    PK(pk.f32(v + "label_conv.weight", c.label_len, &h->wconv));
+    PK(pk.f32(v + "label_conv.bias", 1, &h->bconv));
+    PK(pk.linear(v + "label_fc.weight", v + "label_fc.bias", H, H, false, &h->label_fc));
+    PK(pk.ln(v + "label_layer_norm.weight", v + "label_layer_norm.bias", H, &h->label_ln));
+    h->layers.resize(c.n_layers);
+    h->r_layers.resize(c.n_r_layers);
+    h->x_layers.resize(c.n_x_layers);
+    for (int i = 0; i < c.n_layers; ++i) {
+      const std::string p = b + "encoder.layer." + std::to_string(i) + ".";
+      PK(pack_torch_att(pk, p + "attention.self.", p + "attention.output.", &h->layers[i].att));
+      PK(pack_torch_ffn(pk, p + "intermediate.", p + "output.", &h->layers[i].ffn));
+    }
+    for (int i = 0; i < c.n_r_layers; ++i) {
+      const std::string p = b + "encoder.r_layers." + std::to_string(i) + ".";
+      PK(pack_torch_att(pk, p + "attention.self.", p + "attention.output.", &h->r_layers[i].att));
+      PK(pack_torch_ffn(pk, p + "intermediate.", p + "output.", &h->r_layers[i].ffn));
+    }
+    for (int i = 0; i < c.n_x_layers; ++i) {
+      const std::string p = b + "encoder.x_layers." + std::to_string(i) + ".";
+      XLayer& X = h->x_layers[i];
+      PK(pack_torch_att(pk, p + "visual_attention.att.", p + "visual_attention.output.", &X.cross));
+      PK(pack_torch_att(pk, p + "lang_self_att.self.", p + "lang_self_att.output.", &X.lang_self));
+      PK(pack_torch_att(pk, p + "visn_self_att.self.", p + "visn_self_att.output.", &X.visn_self));
+      PK(pack_torch_ffn(pk, p + "lang_inter.", p + "lang_output.", &X.lang_ffn));
+      PK(pack_torch_ffn(pk, p + "visn_inter.", p + "visn_output.", &X.visn_ffn));
+    }
+    PK(pk.linear(b + "pooler.dense.weight", b + "pooler.dense.bias", H, H, false, &h->pooler));
+    PK(pk.linear("logit_fc.0.weight", "logit_fc.0.bias", 2 * H, H, false, &h->logit0));
+    PK(pk.ln("logit_fc.2.weight", "logit_fc.2.bias", 2 * H, &h->logit_ln));
+    PK(pk.f32("logit_fc.3.weight", int64_t(2) * 2 * H, &h->logit3_w));
+    PK(pk.f32("logit_fc.3.bias", 2, &h->logit3_b));
+  }
+#undef PK
+done:
+  cudaStreamSynchronize(st);
+  cudaFree(staging);
+  return rc;
+}
+
+static mmr_status alloc_workspace(mmr_handle* h) {
+  const mmr_config& c = h->cfg;
+  const int64_t H = c.hidden, I = c.intermediate, B = c.max_batch, R = c.nbox;
+  int64_t S = c.lq + c.nbox;
+  if (c.model_kind == MMR_MODEL_IMAGEBERT_LDS) S = c.lq + 2 * c.nbox;
+  const int64_t M = B * S;
+  h->rows_max = M;
+  size_t bytes = 0;
+  auto add = [&](size_t n) { bytes += (n + 255) & ~size_t(255); };
+  add(B * R * c.feat_dim * 2);  // f16
+  add(B * R * H * 2);           // t16
+  add(B * R * H * 4);           // tmp32
+  add(M * H * 2);               // x16
+  add(M * H * 4);               // x32
+  add(M * 3 * H * 2);           // qkv16
+  add(M * H * 2);               // ctx16
+  add(M * I * 2);               // h16
+  add(M * 4);                   // key_mask
+  add(B * H * 2);               // pooled16
+  add(B * H * 4);               // pooled32
+  add(B * 2 * H * 4);           // head32
+  add(M * H * 4);               // emb_tap
+  bytes += 4096;
+  MMR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->work.base), bytes));
+  h->work.cap = bytes;
+  h->f16 = h->work.take(B * R * c.feat_dim * 2);
+  h->t16 = h->work.take(B * R * H * 2);
+  h->tmp32 = static_cast<float*>(h->work.take(B * R * H * 4));
+  h->x16 = h->work.take(M * H * 2);
+  h->x32 = static_cast<float*>(h->work.take(M * H * 4));
+  h->qkv16 = h->work.take(M * 3 * H * 2);
+  h->ctx16 = h->work.take(M * H * 2);
+  h->h16 = h->work.take(M * I * 2);
+  h->key_mask = static_cast<int32_t*>(h->work.take(M * 4));
+  h->pooled16 = h->work.take(B * H * 2);
+  h->pooled32 = static_cast<float*>(h->work.take(B * H * 4));
+  h->head32 = static_cast<float*>(h->work.take(B * 2 * H * 4));
+  h->emb_tap = static_cast<float*>(h->work.take(M * H * 4));
+  if (!h->emb_tap) return fail(MMR_ERR_NOMEM, "workspace arena mis-sized");
+  return MMR_OK;
+}
+
+// ------------------------------------------------------------------------------------------ forward pieces
+enum LaunchKind { K_GEMM = 0, K_ATTENTION = 1, K_LAYERNORM = 2, K_ROW = 3 };
+
+struct Ctx {
+  mmr_handle* h;
+  cudaStream_t st;
+  int dt;
+  int H;
+  int launches = 0;
+  uint8_t* x16(int64_t row) const { return static_cast<uint8_t*>(h->x16) + row * H * 2; }
+  float* x32(int64_t row) const { return h->x32 + row * H; }
+  uint8_t* qkv(int64_t row, int part) const {
+    return static_cast<uint8_t*>(h->qkv16) + (row * 3 * H + int64_t(part) * H) * 2;
+  }
+  uint8_t* ctx(int64_t row) const { return static_cast<uint8_t*>(h->ctx16) + row * H * 2; }
+
+  // Bookkeeping after every kernel launch: the launch count behind mmr_launches_per_forward and, when profiling
+  // is on, one event per launch so bench.py can attribute device time to kernels inside the timed step.
+  mmr_status mark(int kind, double flops) {
+    ++launches;
+    if (h->prof_on && h->prof_n < int(h->prof_kind.size())) {
+      MMR_CUDA_OK(cudaEventRecord(h->prof_ev[h->prof_n + 1], st));
+      h->prof_kind[h->prof_n] = kind;
+      h->prof_flops[h->prof_n] = flops;
+      ++h->prof_n;
+    }
+    return MMR_OK;
+  }
+  mmr_status G(const void* A, int64_t lda, const Linear& W, int M, const float* residual, void* out16, int64_t ldo16,
+               float* out32, int act) {
+    MMR_TRY(gemm(A, lda, W.w16, W.k, M, W.n, W.k, W.bias, residual, H, out16, ldo16, out32, H, act, dt, st));
+    return mark(K_GEMM, 2.0 * M * W.n * W.k);
+  }
+  mmr_status LN(float* x, const LNp& p, int rows, void* out16, float* out32, float scale, int accumulate) {
+    MMR_TRY(layernorm(x, H, p.gamma, p.beta, 1e-12f, rows, H, out16, H, out32, H, scale, accumulate, dt, st));
+    return mark(K_LAYERNORM, 0.0);
+  }
+};
+
+// x16[rows] -> qkv16[rows]
+static mmr_status qkv_proj(Ctx& c, const Linear& W, int64_t row0, int rows) {
+  return c.G(c.x16(row0), c.H, W, rows, nullptr, c.qkv(row0, 0), 3 * c.H, nullptr, MMR_ACT_NONE);
+}
+// ctx16[q rows] = softmax(Q K^T / 8 + mask) V with Q from rows q0.., K/V from rows k0..
+static mmr_status attend(Ctx& c, int64_t q0, int Sq, int64_t k0, int Sk, const int32_t* key_mask, int B) {
+  MMR_TRY(attention(c.qkv(q0, 0), 3 * c.H, c.qkv(k0, 1), 3 * c.H, c.qkv(k0, 2), 3 * c.H, key_mask, c.ctx(q0), c.H, B,
+                    Sq, Sk, c.h->cfg.heads, c.dt, c.st));
+  return c.mark(K_ATTENTION, 4.0 * B * Sq * Sk * c.H);
+}
+// x = LN(ctx . Wo^T + bo + x), in place on the residual stream
+static mmr_status out_proj_ln(Ctx& c, const AttBlock& A, int64_t row0, int rows) {
+  MMR_TRY(c.G(c.ctx(row0), c.H, A.out, rows, c.x32(row0), nullptr, 0, c.x32(row0), MMR_ACT_NONE));
+  return c.LN(c.x32(row0), A.ln, rows, c.x16(row0), c.x32(row0), 1.0f, 0);
+}
+// x = LN(act(x W1^T + b1) W2^T + b2 + x)
+static mmr_status ffn_block(Ctx& c, const FfnBlock& F, int64_t row0, int rows) {
+  uint8_t* hbuf = static_cast<uint8_t*>(c.h->h16) + row0 * F.in.n * 2;
+  MMR_TRY(c.G(c.x16(row0), c.H, F.in, rows, nullptr, hbuf, F.in.n, nullptr, c.h->act));
+  MMR_TRY(c.G(hbuf, F.in.n, F.out, rows, c.x32(row0), nullptr, 0, c.x32(row0), MMR_ACT_NONE));
+  return c.LN(c.x32(row0), F.ln, rows, c.x16(row0), c.x32(row0), 1.0f, 0);
+}
+static mmr_status self_att_block(Ctx& c, const AttBlock& A, int64_t row0, int B, int S, const int32_t* key_mask) {
+  MMR_TRY(qkv_proj(c, A.qkv, row0, B * S));
+  MMR_TRY(attend(c, row0, S, row0, S, key_mask, B));
+  return out_proj_ln(c, A, row0, B * S);
+}
+static mmr_status bert_layer(Ctx& c, const Layer& L, int64_t row0, int B, int S, const int32_t* key_mask) {
+  MMR_TRY(self_att_block(c, L.att, row0, B, S, key_mask));
+  return ffn_block(c, L.ffn, row0, B * S);
+}
+
+// first token of every pair: rows b*S of x16 (row stride S*H), pixelbert.py:258-266 / modeling.py:596-608
+static mmr_status pooler(Ctx& c, int B, int S) {
+  mmr_handle* h = c.h;
+  return c.G(h->x16, int64_t(S) * c.H, h->pooler, B, nullptr, h->pooled16, c.H, h->pooled32, MMR_ACT_TANH);
+}
+
+static mmr_status forward_single_stream(Ctx& c, const mmr_inputs* in, int B, float* probs) {
+  mmr_handle* h = c.h;
+  const mmr_config& cfg = h->cfg;
+  const int H = c.H, R = cfg.nbox, Lq = cfg.lq;
+  const bool zk = cfg.model_kind == MMR_MODEL_IMAGEBERT_ZK;
+  const int S = zk ? Lq + R : Lq + 2 * R;
+  MMR_REQUIRE(in->query_ids && in->segment_ids && in->label_ids && in->feats, "mmr_forward: missing input pointer");
+  MMR_TRY(cast16(in->feats, h->f16, int64_t(B) * R * cfg.feat_dim, c.dt, c.st));
+  MMR_TRY(c.mark(K_ROW, 0));
+  const int32_t* mask = nullptr;
+  if (zk) {
+    MMR_REQUIRE(in->boxes && in->len_query && in->num_boxes && in->labels, "mmr_forward(zk): missing input pointer");
+    // feat = ReLU(f . Wc2 + bc2)  (model_triple.py:192-194)
+    MMR_TRY(c.G(h->f16, cfg.feat_dim, h->conv2, B * R, nullptr, nullptr, 0, h->tmp32, MMR_ACT_RELU));
+    MMR_TRY(zk_region_sum(h->tmp32, in->boxes, in->label_ids, h->tables, cfg.vocab, h->bc1, h->Wb, h->bb, h->t16,
+                          B * R, c.dt, c.st));
+    MMR_TRY(c.mark(K_ROW, 0));
+    // region = (label + box + feat) . Wfe + bfe  (pixelbert.py:449-452)
+    MMR_TRY(c.G(h->t16, H, h->featureemb, B * R, nullptr, nullptr, 0, h->tmp32, MMR_ACT_NONE));
+    MMR_TRY(zk_embed(in->query_ids, in->segment_ids, h->tmp32, in->len_query, in->num_boxes, h->E, h->T, h->P,
+                     h->emb_ln.gamma, h->emb_ln.beta, Lq, R, B, h->x16, h->x32, h->key_mask, c.dt, c.st));
+    MMR_TRY(c.mark(K_ROW, 0));
+    mask = h->key_mask;
+  } else {
+    // region = f . Wf + bf, no activation (pixelmodel.py:439-442)
+    MMR_TRY(c.G(h->f16, cfg.feat_dim, h->lds_feat, B * R, nullptr, nullptr, 0, h->tmp32, MMR_ACT_NONE));
+    MMR_TRY(lds_embed(in->query_ids, in->segment_ids, in->label_ids, h->tmp32, h->E, h->T, h->P, h->emb_ln.gamma,
+                      h->emb_ln.beta, h->wl, Lq, R, B, h->x16, h->x32, c.dt, c.st));
+    MMR_TRY(c.mark(K_ROW, 0));
+  }
+  if (h->keep_taps)
+    MMR_CUDA_OK(cudaMemcpyAsync(h->emb_tap, h->x32, size_t(B) * S * H * 4, cudaMemcpyDeviceToDevice, c.st));
+  for (const Layer& L : h->layers) MMR_TRY(bert_layer(c, L, 0, B, S, mask));
+  MMR_TRY(pooler(c, B, S));
+  if (zk)
+    MMR_TRY(zk_head(h->pooled32, h->am_wn, in->labels, B, probs, c.st));
+  else
+    MMR_TRY(linear_head(h->pooled32, H, nullptr, nullptr, h->cls_w, h->cls_b, B, probs, c.st));
+  return c.mark(K_ROW, 0);
+}
+
+static mmr_status forward_lxmert(Ctx& c, const mmr_inputs* in, int B, float* probs) {
+  mmr_handle* h = c.h;
+  const mmr_config& cfg = h->cfg;
+  const int H = c.H, R = cfg.nbox, Lq = cfg.lq;
+  MMR_REQUIRE(in->query_ids && in->label_ids && in->feats && in->boxes && in->query_mask && in->visn_mask,
+              "mmr_forward(lxmert): missing input pointer");
+  const int64_t v0 = int64_t(B) * Lq;  // first visual row
+  const int nl = B * Lq, nv = B * R;
+  // language embedding (modeling.py:913)
+  MMR_TRY(lx_lang_embed(in->query_ids, h->E, h->T, h->P, h->emb_ln.gamma, h->emb_ln.beta, Lq, B, c.x16(0), c.x32(0),
+                        c.dt, c.st));
+  MMR_TRY(c.mark(K_ROW, 0));
+  // visual embedding (modeling.py:519-533): (LN(fc(f)) + LN(fc(box)) + LN(fc(conv(label_emb)))) / 3
+  const float third = 1.0f / 3.0f;
+  MMR_TRY(cast16(in->feats, h->f16, int64_t(nv) * cfg.feat_dim, c.dt, c.st));
+  MMR_TRY(c.mark(K_ROW, 0));
+  MMR_TRY(c.G(h->f16, cfg.feat_dim, h->visn_fc, nv, nullptr, nullptr, 0, h->tmp32, MMR_ACT_NONE));
+  MMR_TRY(c.LN(h->tmp32, h->visn_ln, nv, nullptr, c.x32(v0), third, 0));
+  MMR_TRY(lx_box_ln(in->boxes, h->box_w, h->box_b, h->box_ln.gamma, h->box_ln.beta, third, nv, c.x32(v0), c.st));
+  MMR_TRY(c.mark(K_ROW, 0));
+  MMR_TRY(lx_label_z(in->label_ids, h->E, h->T, h->P, h->emb_ln.gamma, h->emb_ln.beta, h->wconv, h->bconv, nv, h->t16,
+                     c.dt, c.st));
+  MMR_TRY(c.mark(K_ROW, 0));
+  MMR_TRY(c.G(h->t16, H, h->label_fc, nv, nullptr, nullptr, 0, h->tmp32, MMR_ACT_NONE));
+  MMR_TRY(c.LN(h->tmp32, h->label_ln, nv, c.x16(v0), c.x32(v0), third, 1));
+  if (h->keep_taps)
+    MMR_CUDA_OK(cudaMemcpyAsync(h->emb_tap, h->x32, size_t(nl + nv) * H * 4, cudaMemcpyDeviceToDevice, c.st));
+  for (const Layer& L : h->layers) MMR_TRY(bert_layer(c, L, 0, B, Lq, in->query_mask));       // modeling.py:577-578
+  for (const Layer& L : h->r_layers) MMR_TRY(bert_layer(c, L, v0, B, R, in->visn_mask));      // :582-583
+  for (const XLayer& X : h->x_layers) {                                                       // :589-591
+    // cross attention both ways with ONE weight set, both from the pre-update streams (modeling.py:462-463)
+    MMR_TRY(qkv_proj(c, X.cross.qkv, 0, nl + nv));
+    MMR_TRY(attend(c, 0, Lq, v0, R, in->visn_mask, B));
+    MMR_TRY(attend(c, v0, R, 0, Lq, in->query_mask, B));
+    MMR_TRY(out_proj_ln(c, X.cross, 0, nl + nv));
+    MMR_TRY(self_att_block(c, X.lang_self, 0, B, Lq, in->query_mask));
+    MMR_TRY(self_att_block(c, X.visn_self, v0, B, R, in->visn_mask));
+    MMR_TRY(ffn_block(c, X.lang_ffn, 0, nl));
+    MMR_TRY(ffn_block(c, X.visn_ffn, v0, nv));
+  }
+  MMR_TRY(pooler(c, B, Lq));
+  // logit_fc: Linear(768,1536) -> erf-GELU -> LayerNorm(1536) -> Linear(1536,2)  (kdd_model.py:167-172)
+  MMR_TRY(gemm(h->pooled16, H, h->logit0.w16, H, B, 2 * H, H, h->logit0.bias, nullptr, 0, nullptr, 0, h->head32, 2 * H,
+               MMR_ACT_GELU_ERF, c.dt, c.st));
+  MMR_TRY(c.mark(K_GEMM, 2.0 * B * 2 * H * H));
+  MMR_TRY(linear_head(h->head32, 2 * H, h->logit_ln.gamma, h->logit_ln.beta, h->logit3_w, h->logit3_b, B, probs,
+                      c.st));
+  return c.mark(K_ROW, 0);
+}
+
+}  // namespace mmr
+
+// ------------------------------------------------------------------------------------------ C ABI
+extern "C" mmr_status mmr_create(const mmr_config* cfg, const mmr_tensor* weights, int n_weights, int device,
+                                 mmr_handle** out) {
+  using namespace mmr;
+  MMR_REQUIRE(cfg && weights && out && n_weights > 0, "mmr_create: null argument");
+  *out = nullptr;
+  MMR_TRY(mmr_device_check(device));
+  MMR_CUDA_OK(cudaSetDevice(device));
+  MMR_REQUIRE(cfg->hidden == 768 && cfg->heads == 12, "mmr_create: only hidden=768 / heads=12 (bert_config.json) is built");
+  MMR_REQUIRE(cfg->intermediate % 64 == 0 && cfg->intermediate % 16 == 0, "mmr_create: intermediate must be a multiple of 64");
+  MMR_REQUIRE(cfg->feat_dim % 64 == 0, "mmr_create: feat_dim must be a multiple of 64");
+  MMR_REQUIRE(cfg->label_len == 8, "mmr_create: label_len must be 8 (8-tap label conv / Conv2d(8,1,1))");
+  MMR_REQUIRE(cfg->dtype == MMR_DT_BF16 || cfg->dtype == MMR_DT_FP16, "mmr_create: bad dtype");
+  MMR_REQUIRE(cfg->model_kind >= 0 && cfg->model_kind <= 2, "mmr_create: bad model_kind %d", cfg->model_kind);
+  MMR_REQUIRE(cfg->lq > 0 && cfg->nbox > 0 && cfg->max_batch > 0, "mmr_create: lq / nbox / max_batch must be positive");
+  const int S = cfg->model_kind == MMR_MODEL_IMAGEBERT_LDS ? cfg->lq + 2 * cfg->nbox : cfg->lq + cfg->nbox;
+  MMR_REQUIRE((cfg->model_kind == MMR_MODEL_LXMERT ? std::max(cfg->lq, cfg->nbox) : S) <= 128,
+              "mmr_create: sequence longer than 128 tokens is not supported by the attention kernel");
+  MMR_REQUIRE(cfg->lq + 1 <= cfg->max_pos, "mmr_create: lq exceeds max_pos");
+  if (cfg->model_kind == MMR_MODEL_LXMERT)
+    MMR_REQUIRE(cfg->n_layers >= 0 && cfg->n_r_layers >= 0 && cfg->n_x_layers >= 0, "mmr_create: negative layer count");
+
+  mmr_handle* h = new mmr_handle();
+  h->cfg = *cfg;
+  h->device = device;
+  TensorMap tm;
+  for (int i = 0; i < n_weights; ++i)
+    if (weights[i].name) tm[weights[i].name] = &weights[i];
+  mmr_status rc = MMR_OK;
+  const size_t wbytes = weight_arena_bytes(*cfg);
+  if (cudaMalloc(reinterpret_cast<void**>(&h->weights.base), wbytes) != cudaSuccess) {
+    rc = fail(MMR_ERR_NOMEM, "cannot allocate %zu bytes for weights", wbytes);
+  } else {
+    h->weights.cap = wbytes;
+    cudaStream_t st;
+    if (cudaStreamCreate(&st) != cudaSuccess) {
+      rc = fail(MMR_ERR_CUDA, "cudaStreamCreate failed");
+    } else {
+      rc = pack_weights(h, tm, st);
+      cudaStreamDestroy(st);
+    }
+  }
+  if (rc == MMR_OK) rc = alloc_workspace(h);
+  if (rc != MMR_OK) {
+    mmr_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return MMR_OK;
+}
+
+extern "C" void mmr_destroy(mmr_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->weights.base) cudaFree(h->weights.base);
+  if (h->work.base) cudaFree(h->work.base);
+  for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+  delete h;
+}
+
+extern "C" mmr_status mmr_forward(mmr_handle* h, const mmr_inputs* in, int B, float* probs_out, float* pooled_out,
+                                  void* stream) {
+  using namespace mmr;
+  MMR_REQUIRE(h && in && probs_out, "mmr_forward: null argument");
+  MMR_REQUIRE(B > 0 && B <= h->cfg.max_batch, "mmr_forward: B=%d outside (0, max_batch=%d]", B, h->cfg.max_batch);
+  MMR_TRY(require_sm100());
+  Ctx c{h, static_cast<cudaStream_t>(stream), h->cfg.dtype, h->cfg.hidden};
+  if (h->prof_on) {
+    h->prof_n = 0;
+    MMR_CUDA_OK(cudaEventRecord(h->prof_ev[0], c.st));
+  }
+  mmr_status rc = h->cfg.model_kind == MMR_MODEL_LXMERT ? forward_lxmert(c, in, B, probs_out)
+                                                        : forward_single_stream(c, in, B, probs_out);
+  if (rc != MMR_OK) return rc;
+  if (pooled_out != nullptr)
+    MMR_CUDA_OK(cudaMemcpyAsync(pooled_out, h->pooled32, size_t(B) * h->cfg.hidden * 4, cudaMemcpyDeviceToDevice,
+                                c.st));
+  h->last_B = B;
+  h->launches = c.launches;
+  return MMR_OK;
+}
+
+extern "C" mmr_status mmr_set_debug_taps(mmr_handle* h, int enable) {
+  MMR_REQUIRE(h, "mmr_set_debug_taps: null handle");
+  h->keep_taps = enable ? 1 : 0;
+  return MMR_OK;
+}
+
+extern "C" mmr_status mmr_get_activation(mmr_handle* h, int which, float* dst, int64_t n_floats, void* stream) {
+  using namespace mmr;
+  MMR_REQUIRE(h && dst, "mmr_get_activation: null argument");
+  MMR_REQUIRE(h->last_B > 0, "mmr_get_activation: no forward has run yet");
+  const mmr_config& c = h->cfg;
+  int64_t S = c.lq + c.nbox;
+  if (c.model_kind == MMR_MODEL_IMAGEBERT_LDS) S = c.lq + 2 * c.nbox;
+  const int64_t have = int64_t(h->last_B) * S * c.hidden;
+  MMR_REQUIRE(n_floats > 0 && n_floats <= have, "mmr_get_activation: n_floats=%lld exceeds %lld", (long long)n_floats,
+              (long long)have);
+  const float* src = nullptr;
+  if (which == 0) {
+    MMR_REQUIRE(h->keep_taps, "mmr_get_activation: embedding tap needs mmr_set_debug_taps(h, 1) before the forward");
+    src = h->emb_tap;
+  } else if (which == 1) {
+    src = h->x32;
+  } else {
+    return fail(MMR_ERR_INVALID, "mmr_get_activation: unknown tap %d", which);
+  }
+  MMR_CUDA_OK(cudaMemcpyAsync(dst, src, size_t(n_floats) * 4, cudaMemcpyDeviceToDevice,
+                              static_cast<cudaStream_t>(stream)));
+  return MMR_OK;
+}
+
+extern "C" mmr_status mmr_set_profiling(mmr_handle* h, int enable) {
+  using namespace mmr;
+  MMR_REQUIRE(h, "mmr_set_profiling: null handle");
+  if (enable && h->prof_ev.empty()) {
+    const int cap = 512;
+    h->prof_ev.resize(cap + 1);
+    for (auto& e : h->prof_ev) MMR_CUDA_OK(cudaEventCreate(&e));
+    h->prof_kind.assign(cap, 0);
+    h->prof_flops.assign(cap, 0.0);
+  }
+  h->prof_on = enable ? 1 : 0;
+  h->prof_n = 0;
+  return MMR_OK;
+}
+
+extern "C" int mmr_get_profile(mmr_handle* h, int cap, int32_t* kinds, float* ms, double* flops) {
+  if (!h || h->prof_n == 0) return 0;
+  if (cudaEventSynchronize(h->prof_ev[h->prof_n]) != cudaSuccess) return -1;
+  const int n = h->prof_n < cap ? h->prof_n : cap;
+  for (int i = 0; i < n; ++i) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, h->prof_ev[i], h->prof_ev[i + 1]) != cudaSuccess) return -1;
+    if (kinds) kinds[i] = h->prof_kind[i];
+    if (ms) ms[i] = t;
+    if (flops) flops[i] = h->prof_flops[i];
+  }
+  return n;
+}
+
+extern "C" int mmr_launches_per_forward(const mmr_handle* h) { return h ? h->launches : 0; }

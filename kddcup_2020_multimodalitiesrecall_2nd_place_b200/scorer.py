@@ -1,0 +1,234 @@
+"""Host side of the scorer: owns one mmr_handle (packed weights + workspace on one GPU) and moves batches through it.
+
+PyTorch is used for device memory, pinned host memory and streams only; every arithmetic step is a kernel of
+libmmrecall.so reached through the C ABI (include/mmrecall.h).  No CPU fallback exists: constructing a
+MatchScorer without the library or without an sm_100 device raises.
+
+Reference call sites replaced (the per-batch body of the three scoring drivers):
+  imagebert_zk/evaluate_normal.py:222-249            sess.run([probs, total_loss], feed_dict)
+  imagebert_lds/src/run_pretraining_predict_score.py:566-576
+  lxmert/src/tasks/kdd_model.py:66-113               KDD.predict inner loop
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import KIND_CODE, LDS, LXMERT, ZK, ModelConfig
+
+_DT = {"fp16": _lib.DT_FP16, "float16": _lib.DT_FP16, "bf16": _lib.DT_BF16, "bfloat16": _lib.DT_BF16}
+
+# feed name -> (mmr_inputs member, torch dtype, trailing shape as a function of cfg)
+_FEEDS = {
+    ZK: ("query_ids", "segment_ids", "label_ids", "feats", "boxes", "len_query", "num_boxes", "labels"),
+    LDS: ("query_ids", "segment_ids", "label_ids", "feats"),
+    LXMERT: ("query_ids", "label_ids", "feats", "boxes", "query_mask", "visn_mask"),
+}
+
+
+def feed_spec(cfg: ModelConfig) -> Dict[str, tuple]:
+    """name -> (torch dtype, per-pair shape) of every device input of `cfg.kind` (reference feeds:
+    evaluate_normal.py:141-152, run_pretraining_predict_score.py:526-541, kdd_model.py:74-95)."""
+    Lq, R, T = cfg.lq, cfg.nbox, cfg.label_len
+    spec = {
+        "query_ids": (torch.int32, (Lq,)),
+        "label_ids": (torch.int32, (R, T)),
+        "feats": (torch.float32, (R, cfg.feat_dim)),
+    }
+    if cfg.kind == ZK:
+        spec.update(segment_ids=(torch.int32, (Lq + R,)), boxes=(torch.float32, (R, 5)), len_query=(torch.int32, ()),
+                    num_boxes=(torch.int32, ()), labels=(torch.int32, ()))
+    elif cfg.kind == LDS:
+        spec.update(segment_ids=(torch.int32, (Lq,)))
+    else:
+        spec.update(boxes=(torch.float32, (R, 4)), query_mask=(torch.int32, (Lq,)), visn_mask=(torch.int32, (R,)))
+    return {k: spec[k] for k in _FEEDS[cfg.kind]}
+
+
+class MatchScorer:
+    """One model (zk / lds / lxmert) resident on one B200."""
+
+    def __init__(self, cfg: ModelConfig, weights: Dict[str, np.ndarray], device: int = 0, dtype: str = "fp16",
+                 max_batch: int = 256):
+        self.lib = _lib.load()
+        self.cfg = cfg
+        self.device = torch.device("cuda", device)
+        self.max_batch = int(max_batch)
+        self.dtype = dtype
+        _lib.check(self.lib.mmr_device_check(device))
+        c = _lib.MmrConfig(
+            model_kind=KIND_CODE[cfg.kind], dtype=_DT[dtype], hidden=cfg.hidden, heads=cfg.heads,
+            intermediate=cfg.intermediate, vocab=cfg.vocab, max_pos=cfg.max_pos, type_vocab=cfg.type_vocab,
+            feat_dim=cfg.feat_dim, label_len=cfg.label_len, n_layers=cfg.n_layers, n_r_layers=cfg.n_r_layers,
+            n_x_layers=cfg.n_x_layers, lq=cfg.lq, nbox=cfg.nbox, max_batch=self.max_batch)
+        keep = []
+        arr = (_lib.MmrTensor * len(weights))()
+        for i, (name, w) in enumerate(weights.items()):
+            a = np.ascontiguousarray(w.detach().cpu().numpy() if torch.is_tensor(w) else w, dtype=np.float32)
+            keep.append(a)
+            arr[i].name = name.encode()
+            arr[i].data = a.ctypes.data
+            arr[i].ndim = min(a.ndim, 4)
+            dims = list(a.shape) if a.ndim <= 4 else [int(np.prod(a.shape[:-3]))] + list(a.shape[-3:])
+            for j, d in enumerate(dims):
+                arr[i].dims[j] = d
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mmr_create(C.byref(c), arr, len(weights), device, C.byref(h)))
+        self._h = h
+        self.spec = feed_spec(cfg)
+        self._slots = None
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.mmr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ device-resident path
+    def _check_feed(self, name, t, B):
+        dt, shape = self.spec[name]
+        if t.dtype != dt or tuple(t.shape) != (B, *shape) or not t.is_contiguous():
+            raise ValueError(f"feed '{name}': need contiguous {dt} {(B, *shape)}, got {t.dtype} {tuple(t.shape)}")
+
+    def forward_device(self, feeds: Dict[str, torch.Tensor], probs_out: Optional[torch.Tensor] = None,
+                       pooled_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Scores B <= max_batch pairs whose feeds already live on this GPU; asynchronous on the current stream.
+        Returns probs [B,2] fp32 (the reference score is probs[:, 1])."""
+        B = feeds["query_ids"].shape[0]
+        inp = _lib.MmrInputs()
+        for name in self.spec:
+            t = feeds[name]
+            self._check_feed(name, t, B)
+            setattr(inp, name, t.data_ptr())
+        if probs_out is None:
+            probs_out = torch.empty((B, 2), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.mmr_forward(self._h, C.byref(inp), B, probs_out.data_ptr(),
+                                        0 if pooled_out is None else pooled_out.data_ptr(),
+                                        torch.cuda.current_stream(self.device).cuda_stream))
+        return probs_out
+
+    def launches_per_forward(self) -> int:
+        return int(self.lib.mmr_launches_per_forward(self._h))
+
+    def set_profiling(self, on: bool):
+        """Per-launch CUDA-event timing inside forward_device (bench.py's roofline line)."""
+        _lib.check(self.lib.mmr_set_profiling(self._h, int(on)))
+
+    def profile(self):
+        """[(kind, ms, flops)] of the last forward; kind 0 GEMM, 1 attention, 2 LayerNorm, 3 embed/head rows."""
+        cap = 512
+        kinds, ms, fl = (C.c_int32 * cap)(), (C.c_float * cap)(), (C.c_double * cap)()
+        n = self.lib.mmr_get_profile(self._h, cap, kinds, ms, fl)
+        if n < 0:
+            raise _lib.MmrError("mmr_get_profile failed")
+        return [(int(kinds[i]), float(ms[i]), float(fl[i])) for i in range(n)]
+
+    def set_debug_taps(self, on: bool):
+        _lib.check(self.lib.mmr_set_debug_taps(self._h, int(on)))
+
+    def activation(self, which: int, batch: int) -> torch.Tensor:
+        """Parity tap after the last forward: 0 = embedding output, 1 = final encoder output; [rows, hidden]."""
+        cfg = self.cfg
+        rows = batch * (cfg.lq + (2 if cfg.kind == LDS else 1) * cfg.nbox)
+        out = torch.empty((rows, cfg.hidden), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.mmr_get_activation(self._h, which, out.data_ptr(), out.numel(),
+                                               torch.cuda.current_stream(self.device).cuda_stream))
+        return out
+
+    # ------------------------------------------------------------------ host-buffer path (what a driver calls)
+    def to_feeds(self, arrays: Dict[str, np.ndarray]) -> Dict[str, torch.Tensor]:
+        """Host arrays (any int width / float32) -> CPU tensors in the exact feed dtypes, pinned."""
+        out = {}
+        for name, (dt, _) in self.spec.items():
+            a = arrays[name]
+            t = a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))
+            t = t.to(dt).contiguous()
+            out[name] = t if t.is_pinned() else t.pin_memory()
+        return out
+
+    def _make_slots(self):
+        if self._slots is None:
+            Bm = self.max_batch
+            self._slots = []
+            for _ in range(2):
+                dev = {n: torch.empty((Bm, *shape), dtype=dt, device=self.device) for n, (dt, shape) in self.spec.items()}
+                self._slots.append({"dev": dev, "free": torch.cuda.Event(), "ready": torch.cuda.Event()})
+            self._copy_stream = torch.cuda.Stream(self.device)
+        return self._slots
+
+    def score(self, feeds_host: Dict[str, torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Scores N pairs held in (ideally pinned) host tensors: N is cut into max_batch chunks whose H2D copies run on
+        a copy stream, double-buffered against the kernels of the previous chunk; probabilities come back to pinned
+        host memory.  Returns probs [N,2] (CPU, pinned); synchronises once at the end."""
+        N = feeds_host["query_ids"].shape[0]
+        if out is None:
+            out = torch.empty((N, 2), dtype=torch.float32).pin_memory()
+        if N == 0:
+            return out
+        slots = self._make_slots()
+        compute = torch.cuda.current_stream(self.device)
+        copy = self._copy_stream
+        copy.wait_stream(compute)
+        dev_probs = torch.empty((N, 2), dtype=torch.float32, device=self.device)
+        Bm = self.max_batch
+        for i, lo in enumerate(range(0, N, Bm)):
+            hi = min(N, lo + Bm)
+            s = slots[i % 2]
+            with torch.cuda.stream(copy):
+                if i >= 2:
+                    copy.wait_event(s["free"])            # kernels of chunk i-2 have consumed this slot
+                for name in self.spec:
+                    s["dev"][name][: hi - lo].copy_(feeds_host[name][lo:hi], non_blocking=True)
+                s["ready"].record(copy)
+            compute.wait_event(s["ready"])
+            self.forward_device({n: s["dev"][n][: hi - lo] for n in self.spec}, probs_out=dev_probs[lo:hi])
+            s["free"].record(compute)
+        out.copy_(dev_probs, non_blocking=True)
+        compute.synchronize()
+        return out
+
+
+def sharded_score(scorer: MatchScorer, feeds_host: Dict[str, torch.Tensor], rank: int, world: int,
+                  gather: bool = True) -> torch.Tensor:
+    """Embarrassingly parallel scoring of N pairs over `world` ranks (one process per GPU): rank r scores the
+    contiguous range [r*ceil(N/W), (r+1)*ceil(N/W)) and the fp32 scores are concatenated with ONE all-gather
+    (NCCL over NVLink when the process group is nccl; gloo in the CPU tests of the host logic).  Returns the full
+    [N] score vector on every rank (CPU tensor)."""
+    import torch.distributed as dist
+    N = feeds_host["query_ids"].shape[0]
+    lo, hi, per = shard_range(N, rank, world)
+    local = {k: v[lo:hi] for k, v in feeds_host.items() if k in scorer.spec}
+    probs = scorer.score(local) if hi > lo else torch.empty((0, 2))
+    mine = torch.zeros(per, dtype=torch.float32)
+    mine[: hi - lo] = probs[:, 1]
+    if not gather or world == 1:
+        return mine[: hi - lo] if world == 1 else mine
+    return allgather_scores(mine, N, world, scorer.device)
+
+
+def shard_range(n: int, rank: int, world: int):
+    per = (n + world - 1) // world
+    lo = min(n, rank * per)
+    hi = min(n, lo + per)
+    return lo, hi, per
+
+
+def allgather_scores(mine: torch.Tensor, n: int, world: int, device=None) -> torch.Tensor:
+    """The only collective of the design: all-gather of per-rank fp32 score shards (padded to equal length)."""
+    import torch.distributed as dist
+    backend = dist.get_backend()
+    buf = mine.to(device) if backend == "nccl" else mine
+    out = torch.empty(world * buf.numel(), dtype=torch.float32, device=buf.device)
+    dist.all_gather_into_tensor(out, buf)
+    return out[:n].cpu() if backend == "nccl" else out[:n]

@@ -1,0 +1,60 @@
+"""CPU tests of the boundary: the C-ABI library builds, loads, exports every symbol include/mmrecall.h declares,
+and fails loudly (no fallback) without an sm_100 device.  No compute calls here."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from kddcup_2020_multimodalitiesrecall_2nd_place_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "mmrecall.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mmr_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    assert _declared_symbols() == sorted(_lib.EXPORTS)
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.load(build_if_missing=True)
+    for name in _declared_symbols():
+        assert hasattr(lib, name), f"libmmrecall.so does not export {name}"
+    assert lib.mmr_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(_lib.MmrConfig) == 16 * 4
+    assert ctypes.sizeof(_lib.MmrInputs) == 10 * ctypes.sizeof(ctypes.c_void_p)
+    assert ctypes.sizeof(_lib.MmrTensor) == 8 + 8 + 8 + 4 * 8   # name, data, ndim (+pad), dims[4]
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; the refusal path is for CPU-only machines")
+    lib = _lib.load(build_if_missing=True)
+    assert lib.mmr_device_check(0) == 3   # MMR_ERR_ARCH
+    assert b"no CPU fallback" in lib.mmr_last_error()
+    with pytest.raises(_lib.MmrError):
+        _lib.check(lib.mmr_cast16(0, 0, 8, _lib.DT_FP16, 0))
+    from kddcup_2020_multimodalitiesrecall_2nd_place_b200 import synth
+    from kddcup_2020_multimodalitiesrecall_2nd_place_b200.config import LDS, ModelConfig
+    from kddcup_2020_multimodalitiesrecall_2nd_place_b200.scorer import MatchScorer
+    cfg = ModelConfig(LDS, n_layers=1, lq=4, nbox=2, vocab=50)
+    with pytest.raises(_lib.MmrError):
+        MatchScorer(cfg, synth.make_weights(cfg, seed=1), device=0)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "kddcup_2020_multimodalitiesrecall_2nd_place_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
