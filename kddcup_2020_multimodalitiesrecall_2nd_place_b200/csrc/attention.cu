@@ -14,7 +14,6 @@ namespace mmr {
 constexpr int kHeadDim = 64;
 constexpr int kPitch = 72;       // smem row pitch in elements (144 B): conflict-free ldmatrix
 constexpr int kMaxSeq = 128;
-constexpr int kMaxKT = kMaxSeq / 8;
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -26,6 +25,12 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, u
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
                : "r"(addr));
+}
+// 16-byte global -> shared copy without a register stage; src_bytes = 0 zero-fills the destination.
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src),
+               "r"(src_bytes)
+               : "memory");
 }
 template <class E16>
 __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
@@ -43,7 +48,10 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a
   }
 }
 
-template <class E16>
+// kMaxKT = compile-time bound on 8-key score tiles (keys padded to 16): the score / probability fragments live in
+// registers, so instantiating for the actual key count (40 / 72 / 104 / 128) instead of the maximum is what keeps
+// enough CTAs resident per SM to hide the global-load latency of these short, synchronous CTAs.
+template <class E16, int kMaxKT>
 __global__ void __launch_bounds__(256)
 attention_kernel(const typename E16::T* __restrict__ q, int64_t ldq, const typename E16::T* __restrict__ k,
                  int64_t ldk, const typename E16::T* __restrict__ v, int64_t ldv,
@@ -60,30 +68,29 @@ attention_kernel(const typename E16::T* __restrict__ q, int64_t ldq, const typen
   T* sV = sK + SkP * kPitch;
   float* sMask = reinterpret_cast<float*>(sV + SkP * kPitch);  // [SkP] additive mask
 
-  // ---- cooperative load of this (pair, head): 8 x 16-byte chunks per 64-wide row, zero padding rows ----
+  // ---- cooperative load of this (pair, head): 8 x 16-byte chunks per 64-wide row.  cp.async (LDGSTS) puts every
+  // chunk in flight at once, without a register round trip per loop iteration; padding rows are zero-filled
+  // (src-size 0).
   const int tid = threadIdx.x;
-  const uint4 zero4 = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < SqP * 8; i += blockDim.x) {
     const int r = i >> 3, c = (i & 7) * 8;
-    uint4 val = zero4;
-    if (r < Sq) val = *reinterpret_cast<const uint4*>(q + (int64_t(b) * Sq + r) * ldq + h * kHeadDim + c);
-    *reinterpret_cast<uint4*>(sQ + r * kPitch + c) = val;
+    const int rr = r < Sq ? r : 0;
+    cp_async_16(sQ + r * kPitch + c, q + (int64_t(b) * Sq + rr) * ldq + h * kHeadDim + c, r < Sq ? 16 : 0);
   }
   for (int i = tid; i < SkP * 8; i += blockDim.x) {
     const int r = i >> 3, c = (i & 7) * 8;
-    uint4 kv = zero4, vv = zero4;
-    if (r < Sk) {
-      kv = *reinterpret_cast<const uint4*>(k + (int64_t(b) * Sk + r) * ldk + h * kHeadDim + c);
-      vv = *reinterpret_cast<const uint4*>(v + (int64_t(b) * Sk + r) * ldv + h * kHeadDim + c);
-    }
-    *reinterpret_cast<uint4*>(sK + r * kPitch + c) = kv;
-    *reinterpret_cast<uint4*>(sV + r * kPitch + c) = vv;
+    const int rr = r < Sk ? r : 0;
+    const int nbytes = r < Sk ? 16 : 0;
+    cp_async_16(sK + r * kPitch + c, k + (int64_t(b) * Sk + rr) * ldk + h * kHeadDim + c, nbytes);
+    cp_async_16(sV + r * kPitch + c, v + (int64_t(b) * Sk + rr) * ldv + h * kHeadDim + c, nbytes);
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
   for (int i = tid; i < SkP; i += blockDim.x) {
     float m = -INFINITY;  // padding keys (>= Sk) do not exist for the softmax
     if (i < Sk) m = (key_mask == nullptr || key_mask[int64_t(b) * Sk + i] != 0) ? 0.0f : -10000.0f;
     sMask[i] = m;
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
   const int warp = tid >> 5, lane = tid & 31;
@@ -198,12 +205,12 @@ static size_t attention_smem_bytes(int Sq, int Sk) {
   return size_t(SqP + 2 * SkP) * kPitch * 2 + size_t(SkP) * 4;
 }
 
-template <class E16>
+template <class E16, int kMaxKT>
 static mmr_status launch_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                                    int64_t ldv, const int32_t* key_mask, void* out, int64_t ldo, int B, int Sq,
                                    int Sk, int heads, cudaStream_t stream) {
   using T = typename E16::T;
-  auto kern = attention_kernel<E16>;
+  auto kern = attention_kernel<E16, kMaxKT>;
   static bool configured = false;
   if (!configured) {
     MMR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -232,11 +239,20 @@ mmr_status attention(const void* q, int64_t ldq, const void* k, int64_t ldk, con
   MMR_REQUIRE(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(out16) & 3) == 0,
               "mmr_attention: q/k/v must be 16-byte aligned");
-  if (dtype == MMR_DT_BF16)
-    return launch_attention<BF16>(q, ldq, k, ldk, v, ldv, key_mask, out16, ldo, B, Sq, Sk, heads, stream);
-  if (dtype == MMR_DT_FP16)
-    return launch_attention<FP16>(q, ldq, k, ldk, v, ldv, key_mask, out16, ldo, B, Sq, Sk, heads, stream);
-  return fail(MMR_ERR_INVALID, "mmr_attention: bad dtype %d", dtype);
+  MMR_REQUIRE(dtype == MMR_DT_BF16 || dtype == MMR_DT_FP16, "mmr_attention: bad dtype %d", dtype);
+#define MMR_ATT(E, KT) return launch_attention<E, KT>(q, ldq, k, ldk, v, ldv, key_mask, out16, ldo, B, Sq, Sk, heads, stream)
+  const int kt = ((Sk + 15) / 16) * 2;   // 8-key tiles after padding the keys to a multiple of 16
+  if (dtype == MMR_DT_BF16) {
+    if (kt <= 6) MMR_ATT(BF16, 6);
+    if (kt <= 10) MMR_ATT(BF16, 10);
+    if (kt <= 14) MMR_ATT(BF16, 14);
+    MMR_ATT(BF16, 16);
+  }
+  if (kt <= 6) MMR_ATT(FP16, 6);
+  if (kt <= 10) MMR_ATT(FP16, 10);
+  if (kt <= 14) MMR_ATT(FP16, 14);
+  MMR_ATT(FP16, 16);
+#undef MMR_ATT
 }
 
 }  // namespace mmr

@@ -13,45 +13,19 @@
 //   epilogue of tile i overlaps the MMAs of tile i+1), and the static tile schedule.
 #include <cuda.h>
 
-#include "common.cuh"
-#include "ptx.cuh"
+#include <cstdlib>
+
+#include "gemm_common.cuh"
 
 namespace mmr {
 
 constexpr int kBM = 128;       // rows per tile (= UMMA M, one TMEM lane per row)
-constexpr int kBN = 256;       // max columns per tile (= UMMA N); narrower N-tail tiles use UMMA N = 16k
-constexpr int kBK = 64;        // K per stage: 64 x 2 B = one 128-byte swizzle atom row
-constexpr int kUmmaK = 16;     // K per tcgen05.mma for 16-bit operands
 constexpr int kStages = 4;
-constexpr int kEpiWarps = 8;
-constexpr int kThreads = 32 * (2 + kEpiWarps);
-constexpr int kTmemCols = 512;  // 2 accumulators x 256 fp32 columns
+constexpr int kThreads = kGemmThreads;
 constexpr uint32_t kABytes = kBM * kBK * 2;
 constexpr uint32_t kBBytes = kBN * kBK * 2;
 constexpr uint32_t kStageBytes = kABytes + kBBytes;
 constexpr size_t kSmemBytes = 1024 /*align slack*/ + size_t(kStages) * kStageBytes + 256 /*barriers*/;
-
-struct GemmParams {
-  int M, N, K;
-  const float* bias;      // [N] or null
-  const float* residual;  // [M, ldr] or null
-  int64_t ldr;
-  void* out16;            // [M, ldo16] or null
-  int64_t ldo16;
-  float* out32;           // [M, ldo32] or null
-  int64_t ldo32;
-  uint32_t idesc_fmt;     // 0 fp16 / 1 bf16
-  uint32_t w_box_rows;    // rows of the W tensor-map box (256, or N when N < 256)
-};
-
-template <int ACT>
-__device__ __forceinline__ float apply_act(float x) {
-  if constexpr (ACT == MMR_ACT_RELU) return fmaxf(x, 0.0f);
-  if constexpr (ACT == MMR_ACT_GELU_TANH) return gelu_tanh_f(x);
-  if constexpr (ACT == MMR_ACT_GELU_ERF) return gelu_erf_f(x);
-  if constexpr (ACT == MMR_ACT_TANH) return tanh_precise_f(x);
-  return x;
-}
 
 template <int ACT, class E16>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -165,65 +139,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const int row = m_blk * kBM + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
       const uint32_t taddr_row = tmem_base + uint32_t(acc) * kBN + (uint32_t(quarter * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        const int col_in_tile = half * 128 + c * 32;
-        if (col_in_tile >= bn) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld_32x32(taddr_row + uint32_t(col_in_tile), r);
-        tmem_ld_wait();
-        const int col0 = n_blk * kBN + col_in_tile;
-        const int ncols = min(32, bn - col_in_tile);  // multiple of 16 (N % 16 == 0)
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (j < ncols) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-            }
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = apply_act<ACT>(v[j]);
-        if (row_ok) {
-          if (p.residual != nullptr) {
-            const float* rp = p.residual + int64_t(row) * p.ldr + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (j < ncols) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(rp + j));
-                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-              }
-            }
-          }
-          if (p.out32 != nullptr) {
-            float* op = p.out32 + int64_t(row) * p.ldo32 + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (j < ncols) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            }
-          }
-          if (p.out16 != nullptr) {
-            typename E16::T* op = reinterpret_cast<typename E16::T*>(p.out16) + int64_t(row) * p.ldo16 + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (j < ncols) {
-                uint4 q;
-                q.x = E16::pack(v[j], v[j + 1]);
-                q.y = E16::pack(v[j + 2], v[j + 3]);
-                q.z = E16::pack(v[j + 4], v[j + 5]);
-                q.w = E16::pack(v[j + 6], v[j + 7]);
-                *reinterpret_cast<uint4*>(op + j) = q;
-              }
-            }
-          }
-        }
-      }
+      epilogue_warp<ACT, E16>(p, taddr_row, row, n_blk * kBN, bn, half);
       // all of this warp's TMEM reads of accumulator `acc` are complete -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -262,8 +179,9 @@ static EncodeTiledFn get_encode_fn() {
 
 // 2-D map over a row-major 16-bit matrix [rows, cols] with row stride ld (elements); box = 64 x box_rows,
 // 128-byte swizzle (must match umma_desc_k_sw128).
-mmr_status make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld,
+mmr_status make_tmap_2d(void* map_out, const void* base, int64_t rows, int64_t cols, int64_t ld,
                         int box_rows, int dtype) {
+  CUtensorMap* map = static_cast<CUtensorMap*>(map_out);
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return fail(MMR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   const cuuint64_t gdim[2] = {cuuint64_t(cols), cuuint64_t(rows)};
@@ -279,7 +197,7 @@ mmr_status make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int64_
   return MMR_OK;
 }
 
-static int sm_count() {
+int sm_count() {
   static int n = 0;
   if (n == 0) {
     int dev = 0;
@@ -337,6 +255,14 @@ mmr_status gemm(const void* A16, int64_t lda, const void* W16, int64_t ldw, int 
   MMR_REQUIRE(!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "mmr_gemm: bias must be 16-byte aligned");
   MMR_REQUIRE(dtype == MMR_DT_BF16 || dtype == MMR_DT_FP16, "mmr_gemm: bad dtype %d", dtype);
 
+  static const bool pair_enabled = [] {
+    const char* e = getenv("MMR_GEMM_PAIR");   // MMR_GEMM_PAIR=0 forces the single-CTA kernel (A/B measurements)
+    return !(e && e[0] == '0');
+  }();
+  if (pair_enabled && gemm_pair_eligible(M, N, K)) {
+    GemmParams pp{M, N, K, bias, residual, ldr, out16, ldo16, out32, ldo32, uint32_t(dtype), uint32_t(kBN / 2)};
+    return gemm_pair(A16, lda, W16, ldw, pp, act, dtype, stream);
+  }
   CUtensorMap ta, tw;
   MMR_TRY(make_tmap_2d(&ta, A16, M, K, lda, kBM, dtype));
   // Box rows for W: a full 256-row box when N allows it, else exactly N rows (N < 256).
