@@ -146,11 +146,13 @@ mmr_status mmr_create(const mmr_config* cfg, const mmr_tensor* weights, int n_we
 void mmr_destroy(mmr_handle* h);
 
 /* Scores B pairs (B <= max_batch).  probs_out dev fp32 [B,2] (softmax of the 2-way head; the reference
- * score is column 1 — for LXMERT column -1, same thing).  pooled_out dev fp32 [B,hidden] or NULL.
+ * score is column 1 — for LXMERT column -1, same thing).  logits_out dev fp32 [B,2] or NULL: the pre-softmax
+ * values (zk: 30 * margin-adjusted cosines, model_triple.py:81-85; lds: logits, run_pretraining_predict_score.py:
+ * 491-492; lxmert: `logit`, the third return value of KDDModel.forward).  pooled_out dev fp32 [B,hidden] or NULL.
  * Replaces model_triple.model_attention_channel_e (model_triple.py:162-214), bertmodel(...) inference
  * path (run_pretraining_predict_score.py:288-394) and KDDModel.forward (kdd_model.py:183-214). */
-mmr_status mmr_forward(mmr_handle* h, const mmr_inputs* in, int B, float* probs_out, float* pooled_out,
-                       void* stream);
+mmr_status mmr_forward(mmr_handle* h, const mmr_inputs* in, int B, float* probs_out, float* logits_out,
+                       float* pooled_out, void* stream);
 
 /* Debug / parity taps (BertModel.get_embedding_output / get_sequence_output, pixelbert.py:279-309): copies of
  * internal activations after the last forward (dev fp32, rows = pairs x tokens; LXMERT: all language rows, then all

@@ -70,7 +70,7 @@ def load(build_if_missing: bool = False) -> C.CDLL:
         lib.mmr_create.argtypes = [C.POINTER(MmrConfig), C.POINTER(MmrTensor), i32, i32, C.POINTER(vp)]
         lib.mmr_destroy.argtypes = [vp]
         lib.mmr_destroy.restype = None
-        lib.mmr_forward.argtypes = [vp, C.POINTER(MmrInputs), i32, vp, vp, vp]
+        lib.mmr_forward.argtypes = [vp, C.POINTER(MmrInputs), i32, vp, vp, vp, vp]
         lib.mmr_set_debug_taps.argtypes = [vp, i32]
         lib.mmr_get_activation.argtypes = [vp, i32, vp, i64, vp]
         lib.mmr_launches_per_forward.argtypes = [vp]

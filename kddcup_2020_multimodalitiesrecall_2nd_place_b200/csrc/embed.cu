@@ -297,7 +297,7 @@ __device__ __forceinline__ void softmax2(float l0, float l1, float* out) {
 // AM-softmax head (model_triple.py:56-86).  wn = column-normalised am_kernel stored as [2,768].
 __global__ void __launch_bounds__(256)
 zk_head_kernel(const float* __restrict__ pooled, const float* __restrict__ wn, const int32_t* __restrict__ labels,
-               int B, float* __restrict__ probs) {
+               int B, float* __restrict__ probs, float* __restrict__ logits) {
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
   const int lane = threadIdx.x & 31;
@@ -322,6 +322,7 @@ zk_head_kernel(const float* __restrict__ pooled, const float* __restrict__ wn, c
     const float m = g > 0.35f ? 0.35f : 0.f;                // margin only when the fed label's cosine > m
     if (y) c1 -= m; else c0 -= m;
     softmax2(30.f * c0, 30.f * c1, probs + 2 * b);
+    if (logits != nullptr) { logits[2 * b] = 30.f * c0; logits[2 * b + 1] = 30.f * c1; }
   }
 }
 
@@ -329,7 +330,7 @@ zk_head_kernel(const float* __restrict__ pooled, const float* __restrict__ wn, c
 __global__ void __launch_bounds__(256)
 linear_head_kernel(const float* __restrict__ x, int width, const float* __restrict__ ln_gamma,
                    const float* __restrict__ ln_beta, const float* __restrict__ W, const float* __restrict__ bias,
-                   int B, float* __restrict__ probs) {
+                   int B, float* __restrict__ probs, float* __restrict__ logits) {
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
   const int lane = threadIdx.x & 31;
@@ -375,7 +376,10 @@ linear_head_kernel(const float* __restrict__ x, int width, const float* __restri
     }
   }
   d0 = warp_sum(d0); d1 = warp_sum(d1);
-  if (lane == 0) softmax2(d0 + bias[0], d1 + bias[1], probs + 2 * b);
+  if (lane == 0) {
+    softmax2(d0 + bias[0], d1 + bias[1], probs + 2 * b);
+    if (logits != nullptr) { logits[2 * b] = d0 + bias[0]; logits[2 * b + 1] = d1 + bias[1]; }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- launchers
@@ -448,17 +452,17 @@ mmr_status lx_box_ln(const float* boxes4, const float* Wb, const float* bb, cons
   return MMR_OK;
 }
 
-mmr_status zk_head(const float* pooled, const float* wn, const int32_t* labels, int B, float* probs,
+mmr_status zk_head(const float* pooled, const float* wn, const int32_t* labels, int B, float* probs, float* logits,
                    cudaStream_t st) {
-  zk_head_kernel<<<blocks_for(B), 256, 0, st>>>(pooled, wn, labels, B, probs);
+  zk_head_kernel<<<blocks_for(B), 256, 0, st>>>(pooled, wn, labels, B, probs, logits);
   MMR_CUDA_OK(cudaGetLastError());
   return MMR_OK;
 }
 
 mmr_status linear_head(const float* x, int width, const float* ln_gamma, const float* ln_beta, const float* W,
-                       const float* bias, int B, float* probs, cudaStream_t st) {
+                       const float* bias, int B, float* probs, float* logits, cudaStream_t st) {
   MMR_REQUIRE(width % 128 == 0 && width <= 1536, "linear_head: width %d unsupported", width);
-  linear_head_kernel<<<blocks_for(B), 256, 0, st>>>(x, width, ln_gamma, ln_beta, W, bias, B, probs);
+  linear_head_kernel<<<blocks_for(B), 256, 0, st>>>(x, width, ln_gamma, ln_beta, W, bias, B, probs, logits);
   MMR_CUDA_OK(cudaGetLastError());
   return MMR_OK;
 }

@@ -25,7 +25,7 @@ constexpr int kPairStages = 6;
 constexpr uint32_t kPairABytes = kHalfM * kBK * 2;   // 16 KB
 constexpr uint32_t kPairBBytes = kHalfN * kBK * 2;   // 16 KB
 constexpr uint32_t kPairStageBytes = kPairABytes + kPairBBytes;
-constexpr size_t kPairSmemBytes = 1024 + size_t(kPairStages) * kPairStageBytes + 256;
+constexpr size_t kPairSmemBytes = 1024 + size_t(kPairStages) * kPairStageBytes + 256 + kEpiSmemBytes;
 
 template <int ACT, class E16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
@@ -41,6 +41,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* tfull_bar = bars + 2 * kPairStages;   // [2]       MMA -> epilogue, multicast to both CTAs
   uint64_t* tempty_bar = tfull_bar + 2;           // [2]       epilogue (both CTAs) -> MMA; used in the leader only
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* epi_stage = reinterpret_cast<float*>(smem + size_t(kPairStages) * kPairStageBytes + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -135,9 +136,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const uint32_t acc_phase = (it >> 1) & 1u;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = m_blk * kPairBM + int(rank) * kHalfM + quarter * 32 + lane;
+      const int row0 = m_blk * kPairBM + int(rank) * kHalfM + quarter * 32;
       const uint32_t taddr_row = tmem_base + uint32_t(acc) * kBN + (uint32_t(quarter * 32) << 16);
-      epilogue_warp<ACT, E16>(p, taddr_row, row, n_blk * kBN, kBN, half);
+      epilogue_warp<ACT, E16>(p, taddr_row, row0, n_blk * kBN, kBN, half, epi_stage + ew * kEpiStageFloats);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));

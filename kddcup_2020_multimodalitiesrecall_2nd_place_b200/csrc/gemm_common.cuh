@@ -35,69 +35,96 @@ __device__ __forceinline__ float apply_act(float x) {
   return x;
 }
 
-// One epilogue warp's share of a 128-row x bn-column accumulator: lanes [32*quarter, +32) (one row per thread),
-// columns [128*half, 128*half + 128) in chunks of 32.  `taddr_row` already carries the lane and accumulator offsets.
+constexpr int kEpiStageFloats = 32 * 32;                       // one 32-row x 32-column fp32 chunk per warp
+constexpr int kEpiSmemBytes = kEpiWarps * kEpiStageFloats * 4;  // 32 KB
+
+// One epilogue warp's share of a 128-row x bn-column accumulator: TMEM lanes [32*quarter, +32), columns
+// [128*half, 128*half + 128) in chunks of 32.  `taddr_row` carries the lane and accumulator offsets, `row0` is the
+// global row of lane 0.
+//
+// TMEM hands every thread one ROW of the chunk, which is the worst possible shape for global memory (each warp
+// instruction would touch 32 different 128-byte lines).  So: phase 1 applies bias + activation per row and parks the
+// chunk in this warp's shared-memory stage (XOR-swizzled float4 slots, conflict-free both ways); phase 2 re-reads
+// it row-major, so that every global instruction of the residual read and of the fp32 / 16-bit stores covers
+// whole contiguous row segments (4 rows x 128 B, or 8 rows x 64 B on the 16-bit-only path).
 template <int ACT, class E16>
-__device__ __forceinline__ void epilogue_warp(const GemmParams& p, uint32_t taddr_row, int row, int col_tile0, int bn,
-                                              int half) {
-  const bool row_ok = row < p.M;
+__device__ __forceinline__ void epilogue_warp(const GemmParams& p, uint32_t taddr_row, int row0, int col_tile0, int bn,
+                                              int half, float* stage) {
+  const int lane = threadIdx.x & 31;
+  const bool only16 = p.out32 == nullptr && p.residual == nullptr;
 #pragma unroll 1
-for (int c = 0; c < 4; ++c) {
-  const int col_in_tile = half * 128 + c * 32;
-  if (col_in_tile >= bn) break;  // warp-uniform
-  uint32_t r[32];
-  tmem_ld_32x32(taddr_row + uint32_t(col_in_tile), r);
-  tmem_ld_wait();
-  const int col0 = col_tile0 + col_in_tile;
-  const int ncols = min(32, bn - col_in_tile);  // multiple of 16 (N % 16 == 0)
-  float v[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-  if (p.bias != nullptr) {
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      if (j < ncols) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-      }
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = apply_act<ACT>(v[j]);
-  if (row_ok) {
+  for (int c = 0; c < 4; ++c) {
+    const int col_in_tile = half * 128 + c * 32;
+    if (col_in_tile >= bn) break;  // warp-uniform
+    const int col0 = col_tile0 + col_in_tile;
+    const int ncols = min(32, bn - col_in_tile);  // multiple of 16 (N % 16 == 0)
+    // Residual rows of phase 2, fetched first so that their L2 latency hides behind the TMEM load and phase 1.
+    // (out32 may alias residual — the model driver updates the residual stream in place — so these loads must be
+    // issued explicitly before any store of this chunk; each element is read and written by the same thread.)
+    float4 res[8];
     if (p.residual != nullptr) {
-      const float* rp = p.residual + int64_t(row) * p.ldr + col0;
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        if (j < ncols) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(rp + j));
-          v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-        }
+      for (int it = 0; it < 8; ++it) {
+        const int grow = row0 + it * 4 + (lane >> 3), c4 = lane & 7;
+        res[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (grow < p.M && 4 * c4 < ncols)
+          res[it] = *reinterpret_cast<const float4*>(p.residual + int64_t(grow) * p.ldr + col0 + 4 * c4);
       }
     }
-    if (p.out32 != nullptr) {
-      float* op = p.out32 + int64_t(row) * p.ldo32 + col0;
+    uint32_t r[32];
+    tmem_ld_32x32(taddr_row + uint32_t(col_in_tile), r);
+    tmem_ld_wait();
+    // ---- phase 1: this thread's row -> bias, activation -> swizzled stage
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        if (j < ncols) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    for (int j = 0; j < 8; ++j) {
+      float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                             __uint_as_float(r[4 * j + 3]));
+      if (p.bias != nullptr && 4 * j < ncols) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * j));
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
       }
+      v.x = apply_act<ACT>(v.x); v.y = apply_act<ACT>(v.y); v.z = apply_act<ACT>(v.z); v.w = apply_act<ACT>(v.w);
+      *reinterpret_cast<float4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) = v;
     }
-    if (p.out16 != nullptr) {
-      typename E16::T* op = reinterpret_cast<typename E16::T*>(p.out16) + int64_t(row) * p.ldo16 + col0;
+    __syncwarp();
+    // ---- phase 2: row-major read-back, coalesced global traffic
+    if (only16) {
+      typename E16::T* o16 = reinterpret_cast<typename E16::T*>(p.out16);
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        if (j < ncols) {
+      for (int it = 0; it < 4; ++it) {
+        const int rl = it * 8 + (lane >> 2), c8 = lane & 3;
+        const float4 x0 = *reinterpret_cast<const float4*>(stage + rl * 32 + (((2 * c8) ^ (rl & 7)) << 2));
+        const float4 x1 = *reinterpret_cast<const float4*>(stage + rl * 32 + (((2 * c8 + 1) ^ (rl & 7)) << 2));
+        const int grow = row0 + rl;
+        if (grow < p.M && 8 * c8 < ncols) {
           uint4 q;
-          q.x = E16::pack(v[j], v[j + 1]);
-          q.y = E16::pack(v[j + 2], v[j + 3]);
-          q.z = E16::pack(v[j + 4], v[j + 5]);
-          q.w = E16::pack(v[j + 6], v[j + 7]);
-          *reinterpret_cast<uint4*>(op + j) = q;
+          q.x = E16::pack(x0.x, x0.y); q.y = E16::pack(x0.z, x0.w);
+          q.z = E16::pack(x1.x, x1.y); q.w = E16::pack(x1.z, x1.w);
+          *reinterpret_cast<uint4*>(o16 + int64_t(grow) * p.ldo16 + col0 + 8 * c8) = q;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int rl = it * 4 + (lane >> 3), c4 = lane & 7;
+        float4 x = *reinterpret_cast<const float4*>(stage + rl * 32 + ((c4 ^ (rl & 7)) << 2));
+        const int grow = row0 + rl;
+        if (grow < p.M && 4 * c4 < ncols) {
+          const int gcol = col0 + 4 * c4;
+          if (p.residual != nullptr) {
+            x.x += res[it].x; x.y += res[it].y; x.z += res[it].z; x.w += res[it].w;
+          }
+          if (p.out32 != nullptr) *reinterpret_cast<float4*>(p.out32 + int64_t(grow) * p.ldo32 + gcol) = x;
+          if (p.out16 != nullptr) {
+            uint2 q;
+            q.x = E16::pack(x.x, x.y); q.y = E16::pack(x.z, x.w);
+            *reinterpret_cast<uint2*>(reinterpret_cast<typename E16::T*>(p.out16) + int64_t(grow) * p.ldo16 + gcol) = q;
+          }
         }
       }
     }
+    __syncwarp();
   }
-}
 }
 
 // 2-D tensor map over a row-major 16-bit matrix [rows, cols] with row stride ld (elements); box = 64 x box_rows,

@@ -25,7 +25,7 @@ constexpr int kThreads = kGemmThreads;
 constexpr uint32_t kABytes = kBM * kBK * 2;
 constexpr uint32_t kBBytes = kBN * kBK * 2;
 constexpr uint32_t kStageBytes = kABytes + kBBytes;
-constexpr size_t kSmemBytes = 1024 /*align slack*/ + size_t(kStages) * kStageBytes + 256 /*barriers*/;
+constexpr size_t kSmemBytes = 1024 /*align slack*/ + size_t(kStages) * kStageBytes + 256 /*barriers*/ + kEpiSmemBytes;
 
 template <int ACT, class E16>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -42,6 +42,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint64_t* tfull_bar = bars + 2 * kStages;  // [2]        MMA -> epilogue
   uint64_t* tempty_bar = tfull_bar + 2;      // [2]        epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* epi_stage = reinterpret_cast<float*>(smem + size_t(kStages) * kStageBytes + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -138,9 +139,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint32_t acc_phase = (it >> 1) & 1u;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = m_blk * kBM + quarter * 32 + lane;
+      const int row0 = m_blk * kBM + quarter * 32;
       const uint32_t taddr_row = tmem_base + uint32_t(acc) * kBN + (uint32_t(quarter * 32) << 16);
-      epilogue_warp<ACT, E16>(p, taddr_row, row, n_blk * kBN, bn, half);
+      epilogue_warp<ACT, E16>(p, taddr_row, row0, n_blk * kBN, bn, half, epi_stage + ew * kEpiStageFloats);
       // all of this warp's TMEM reads of accumulator `acc` are complete -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();

@@ -34,9 +34,9 @@ mmr_status lx_label_z(const int32_t* label_ids, const float* E, const float* T, 
                       void* z16, int dtype, cudaStream_t st);
 mmr_status lx_box_ln(const float* boxes4, const float* Wb, const float* bb, const float* gamma, const float* beta,
                      float scale, int rows, float* acc32, cudaStream_t st);
-mmr_status zk_head(const float* pooled, const float* wn, const int32_t* labels, int B, float* probs,
+mmr_status zk_head(const float* pooled, const float* wn, const int32_t* labels, int B, float* probs, float* logits,
                    cudaStream_t st);
 mmr_status linear_head(const float* x, int width, const float* ln_gamma, const float* ln_beta, const float* W,
-                       const float* bias, int B, float* probs, cudaStream_t st);
+                       const float* bias, int B, float* probs, float* logits, cudaStream_t st);
 
 }  // namespace mmr

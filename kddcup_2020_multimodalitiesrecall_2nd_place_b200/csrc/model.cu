@@ -582,7 +582,7 @@ static mmr_status pooler(Ctx& c, int B, int S) {
   return c.G(h->x16, int64_t(S) * c.H, h->pooler, B, nullptr, h->pooled16, c.H, h->pooled32, MMR_ACT_TANH);
 }
 
-static mmr_status forward_single_stream(Ctx& c, const mmr_inputs* in, int B, float* probs) {
+static mmr_status forward_single_stream(Ctx& c, const mmr_inputs* in, int B, float* probs, float* logits) {
   mmr_handle* h = c.h;
   const mmr_config& cfg = h->cfg;
   const int H = c.H, R = cfg.nbox, Lq = cfg.lq;
@@ -617,13 +617,13 @@ static mmr_status forward_single_stream(Ctx& c, const mmr_inputs* in, int B, flo
   for (const Layer& L : h->layers) MMR_TRY(bert_layer(c, L, 0, B, S, mask));
   MMR_TRY(pooler(c, B, S));
   if (zk)
-    MMR_TRY(zk_head(h->pooled32, h->am_wn, in->labels, B, probs, c.st));
+    MMR_TRY(zk_head(h->pooled32, h->am_wn, in->labels, B, probs, logits, c.st));
   else
-    MMR_TRY(linear_head(h->pooled32, H, nullptr, nullptr, h->cls_w, h->cls_b, B, probs, c.st));
+    MMR_TRY(linear_head(h->pooled32, H, nullptr, nullptr, h->cls_w, h->cls_b, B, probs, logits, c.st));
   return c.mark(K_ROW, 0);
 }
 
-static mmr_status forward_lxmert(Ctx& c, const mmr_inputs* in, int B, float* probs) {
+static mmr_status forward_lxmert(Ctx& c, const mmr_inputs* in, int B, float* probs, float* logits) {
   mmr_handle* h = c.h;
   const mmr_config& cfg = h->cfg;
   const int H = c.H, R = cfg.nbox, Lq = cfg.lq;
@@ -669,7 +669,7 @@ static mmr_status forward_lxmert(Ctx& c, const mmr_inputs* in, int B, float* pro
                MMR_ACT_GELU_ERF, c.dt, c.st));
   MMR_TRY(c.mark(K_GEMM, 2.0 * B * 2 * H * H));
   MMR_TRY(linear_head(h->head32, 2 * H, h->logit_ln.gamma, h->logit_ln.beta, h->logit3_w, h->logit3_b, B, probs,
-                      c.st));
+                      logits, c.st));
   return c.mark(K_ROW, 0);
 }
 
@@ -735,8 +735,8 @@ extern "C" void mmr_destroy(mmr_handle* h) {
   delete h;
 }
 
-extern "C" mmr_status mmr_forward(mmr_handle* h, const mmr_inputs* in, int B, float* probs_out, float* pooled_out,
-                                  void* stream) {
+extern "C" mmr_status mmr_forward(mmr_handle* h, const mmr_inputs* in, int B, float* probs_out, float* logits_out,
+                                  float* pooled_out, void* stream) {
   using namespace mmr;
   MMR_REQUIRE(h && in && probs_out, "mmr_forward: null argument");
   MMR_REQUIRE(B > 0 && B <= h->cfg.max_batch, "mmr_forward: B=%d outside (0, max_batch=%d]", B, h->cfg.max_batch);
@@ -746,8 +746,8 @@ extern "C" mmr_status mmr_forward(mmr_handle* h, const mmr_inputs* in, int B, fl
     h->prof_n = 0;
     MMR_CUDA_OK(cudaEventRecord(h->prof_ev[0], c.st));
   }
-  mmr_status rc = h->cfg.model_kind == MMR_MODEL_LXMERT ? forward_lxmert(c, in, B, probs_out)
-                                                        : forward_single_stream(c, in, B, probs_out);
+  mmr_status rc = h->cfg.model_kind == MMR_MODEL_LXMERT ? forward_lxmert(c, in, B, probs_out, logits_out)
+                                                        : forward_single_stream(c, in, B, probs_out, logits_out);
   if (rc != MMR_OK) return rc;
   if (pooled_out != nullptr)
     MMR_CUDA_OK(cudaMemcpyAsync(pooled_out, h->pooled32, size_t(B) * h->cfg.hidden * 4, cudaMemcpyDeviceToDevice,

@@ -102,7 +102,8 @@ class MatchScorer:
             raise ValueError(f"feed '{name}': need contiguous {dt} {(B, *shape)}, got {t.dtype} {tuple(t.shape)}")
 
     def forward_device(self, feeds: Dict[str, torch.Tensor], probs_out: Optional[torch.Tensor] = None,
-                       pooled_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                       pooled_out: Optional[torch.Tensor] = None,
+                       logits_out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Scores B <= max_batch pairs whose feeds already live on this GPU; asynchronous on the current stream.
         Returns probs [B,2] fp32 (the reference score is probs[:, 1])."""
         B = feeds["query_ids"].shape[0]
@@ -114,6 +115,7 @@ class MatchScorer:
         if probs_out is None:
             probs_out = torch.empty((B, 2), dtype=torch.float32, device=self.device)
         _lib.check(self.lib.mmr_forward(self._h, C.byref(inp), B, probs_out.data_ptr(),
+                                        0 if logits_out is None else logits_out.data_ptr(),
                                         0 if pooled_out is None else pooled_out.data_ptr(),
                                         torch.cuda.current_stream(self.device).cuda_stream))
         return probs_out

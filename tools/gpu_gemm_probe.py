@@ -69,7 +69,8 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "child":
         child()
         sys.exit(0)
-    for pair in ("1", "0"):
+    modes = [a for a in sys.argv[1:] if a in ("0", "1")] or ["1", "0"]
+    for pair in modes:
         env = dict(os.environ, MMR_GEMM_PAIR=pair)
         print(f"===== MMR_GEMM_PAIR={pair}", flush=True)
         try:
