@@ -81,6 +81,17 @@ mmr_status mmr_layernorm(const float* x, int64_t ldx, const float* gamma, const 
                          int H, void* out16, int64_t ldo16, float* out32, int64_t ldo32, float scale,
                          int accumulate, int dtype, void* stream);
 
+/* out = LayerNorm(A[M,K] * W[768,K]^T + bias + residual) * gamma + beta in ONE kernel (cluster of three CTA
+ * pairs, row statistics exchanged through distributed shared memory): the "dense + residual + layer_norm" tails of
+ * pixelbert.py:960-966, 977-983 / modeling.py:355-366, 409-420.  N is fixed at 768; residual fp32 [M, ldr] may
+ * alias out32 (in-place residual stream).  mmr_gemm_layernorm_supported tells whether (M, K) can take this path on
+ * the current device (else call mmr_gemm with a residual, then mmr_layernorm). */
+mmr_status mmr_gemm_layernorm(const void* A16, int64_t lda, const void* W16, int64_t ldw, int M, int K,
+                              const float* bias, const float* residual, int64_t ldr, const float* gamma,
+                              const float* beta, float eps, void* out16, int64_t ldo16, float* out32, int64_t ldo32,
+                              int dtype, void* stream);
+int mmr_gemm_layernorm_supported(int M, int K, int dtype);
+
 /* Multi-head scaled-dot-product attention, softmax in fp32, additive key mask (1-m)*-10000:
  * pixelbert.py:790-850 / modeling.py:325-352.  q [B*Sq, ldq], k/v [B*Sk, ldk/ldv], head h = columns
  * [64h, 64h+64).  key_mask dev int32 [B,Sk] (1 = attend) or NULL.  Sq, Sk <= 128. */
@@ -139,6 +150,9 @@ typedef struct {
   const int32_t* query_mask;  /* lxmert: [B, lq]  input_mask                                      */
   const int32_t* visn_mask;   /* lxmert: [B, nbox] visual_attention_mask                          */
   const int32_t* labels;      /* zk: [B] AM-softmax margin label (model_triple.py:66-81)          */
+  const float* region_sum;    /* zk, optional: [B, nbox, hidden] fp32 = label + box + feat term ALREADY fused
+                                 (the `imgfeat` argument of pixelbert.BertModel, pixelbert.py:150-186); when
+                                 non-NULL, feats / boxes / label_ids are ignored                     */
 } mmr_inputs;
 
 mmr_status mmr_create(const mmr_config* cfg, const mmr_tensor* weights, int n_weights, int device,
@@ -157,7 +171,9 @@ mmr_status mmr_forward(mmr_handle* h, const mmr_inputs* in, int B, float* probs_
 /* Debug / parity taps (BertModel.get_embedding_output / get_sequence_output, pixelbert.py:279-309): copies of
  * internal activations after the last forward (dev fp32, rows = pairs x tokens; LXMERT: all language rows, then all
  * visual rows).  which: 0 = embedding output, only kept when mmr_set_debug_taps(h, 1) was called before the forward
- * (one extra device copy per forward); 1 = final encoder layer output. */
+ * (one extra device copy per forward); 1 = final encoder layer output; 2 + i = output of encoder layer i
+ * (get_all_encoder_layers; single-stream models only), kept when mmr_set_debug_taps(h, 2) was called (allocates
+ * n_layers x rows x hidden floats once, copies after every layer). */
 mmr_status mmr_set_debug_taps(mmr_handle* h, int enable);
 mmr_status mmr_get_activation(mmr_handle* h, int which, float* dst, int64_t n_floats, void* stream);
 

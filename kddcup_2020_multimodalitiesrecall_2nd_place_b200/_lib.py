@@ -15,7 +15,7 @@ MODEL_ZK, MODEL_LDS, MODEL_LXMERT = range(3)
 # every symbol include/mmrecall.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "mmr_last_error", "mmr_abi_version", "mmr_device_check",
-    "mmr_gemm", "mmr_layernorm", "mmr_attention", "mmr_cast16",
+    "mmr_gemm", "mmr_gemm_layernorm", "mmr_gemm_layernorm_supported", "mmr_layernorm", "mmr_attention", "mmr_cast16",
     "mmr_create", "mmr_destroy", "mmr_forward", "mmr_set_debug_taps", "mmr_get_activation",
     "mmr_launches_per_forward", "mmr_set_profiling", "mmr_get_profile",
 ]
@@ -34,7 +34,7 @@ class MmrTensor(C.Structure):
 class MmrInputs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "query_ids", "segment_ids", "label_ids", "feats", "boxes", "len_query", "num_boxes", "query_mask",
-        "visn_mask", "labels")]
+        "visn_mask", "labels", "region_sum")]
 
 
 class MmrError(RuntimeError):
@@ -66,6 +66,8 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.mmr_layernorm.argtypes = [vp, i64, vp, vp, f32, i32, i32, vp, i64, vp, i64, f32, i32, i32, vp]
     lib.mmr_attention.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, i64, i32, i32, i32, i32, i32, vp]
     lib.mmr_cast16.argtypes = [vp, vp, i64, i32, vp]
+    lib.mmr_gemm_layernorm.argtypes = [vp, i64, vp, i64, i32, i32, vp, vp, i64, vp, vp, f32, vp, i64, vp, i64, i32, vp]
+    lib.mmr_gemm_layernorm_supported.argtypes = [i32, i32, i32]
     if True:
         lib.mmr_create.argtypes = [C.POINTER(MmrConfig), C.POINTER(MmrTensor), i32, i32, C.POINTER(vp)]
         lib.mmr_destroy.argtypes = [vp]

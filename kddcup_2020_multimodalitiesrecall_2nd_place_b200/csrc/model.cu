@@ -158,6 +158,7 @@ struct mmr_handle {
   void *f16 = nullptr, *t16 = nullptr, *x16 = nullptr, *qkv16 = nullptr, *ctx16 = nullptr, *h16 = nullptr,
        *pooled16 = nullptr;
   float *tmp32 = nullptr, *x32 = nullptr, *pooled32 = nullptr, *head32 = nullptr, *emb_tap = nullptr;
+  float* layer_tap = nullptr;   // [n_layers, rows_max, hidden], allocated by mmr_set_debug_taps(h, 2)
   int32_t* key_mask = nullptr;
   int64_t rows_max = 0;   // encoder rows at max_batch
   int last_B = 0;
@@ -538,6 +539,16 @@ struct Ctx {
     MMR_TRY(gemm(A, lda, W.w16, W.k, M, W.n, W.k, W.bias, residual, H, out16, ldo16, out32, H, act, dt, st));
     return mark(K_GEMM, 2.0 * M * W.n * W.k);
   }
+  // x32[row0..] = LN(A . W^T + bias + x32[row0..]), x16 mirror: one fused kernel when the shape allows, else two.
+  mmr_status G_LN(const void* A, int64_t lda, const Linear& W, const LNp& ln, int64_t row0, int rows) {
+    if (gemm_ln_eligible(rows, W.n, W.k, dt)) {
+      MMR_TRY(gemm_ln(A, lda, W.w16, W.k, rows, W.k, W.bias, x32(row0), H, ln.gamma, ln.beta, 1e-12f, x16(row0), H,
+                      x32(row0), H, dt, st));
+      return mark(K_GEMM, 2.0 * rows * W.n * W.k);
+    }
+    MMR_TRY(G(A, lda, W, rows, x32(row0), nullptr, 0, x32(row0), MMR_ACT_NONE));
+    return LN(x32(row0), ln, rows, x16(row0), x32(row0), 1.0f, 0);
+  }
   mmr_status LN(float* x, const LNp& p, int rows, void* out16, float* out32, float scale, int accumulate) {
     MMR_TRY(layernorm(x, H, p.gamma, p.beta, 1e-12f, rows, H, out16, H, out32, H, scale, accumulate, dt, st));
     return mark(K_LAYERNORM, 0.0);
@@ -556,15 +567,13 @@ static mmr_status attend(Ctx& c, int64_t q0, int Sq, int64_t k0, int Sk, const i
 }
 // x = LN(ctx . Wo^T + bo + x), in place on the residual stream
 static mmr_status out_proj_ln(Ctx& c, const AttBlock& A, int64_t row0, int rows) {
-  MMR_TRY(c.G(c.ctx(row0), c.H, A.out, rows, c.x32(row0), nullptr, 0, c.x32(row0), MMR_ACT_NONE));
-  return c.LN(c.x32(row0), A.ln, rows, c.x16(row0), c.x32(row0), 1.0f, 0);
+  return c.G_LN(c.ctx(row0), c.H, A.out, A.ln, row0, rows);
 }
 // x = LN(act(x W1^T + b1) W2^T + b2 + x)
 static mmr_status ffn_block(Ctx& c, const FfnBlock& F, int64_t row0, int rows) {
   uint8_t* hbuf = static_cast<uint8_t*>(c.h->h16) + row0 * F.in.n * 2;
   MMR_TRY(c.G(c.x16(row0), c.H, F.in, rows, nullptr, hbuf, F.in.n, nullptr, c.h->act));
-  MMR_TRY(c.G(hbuf, F.in.n, F.out, rows, c.x32(row0), nullptr, 0, c.x32(row0), MMR_ACT_NONE));
-  return c.LN(c.x32(row0), F.ln, rows, c.x16(row0), c.x32(row0), 1.0f, 0);
+  return c.G_LN(hbuf, F.in.n, F.out, F.ln, row0, rows);
 }
 static mmr_status self_att_block(Ctx& c, const AttBlock& A, int64_t row0, int B, int S, const int32_t* key_mask) {
   MMR_TRY(qkv_proj(c, A.qkv, row0, B * S));
@@ -588,17 +597,28 @@ static mmr_status forward_single_stream(Ctx& c, const mmr_inputs* in, int B, flo
   const int H = c.H, R = cfg.nbox, Lq = cfg.lq;
   const bool zk = cfg.model_kind == MMR_MODEL_IMAGEBERT_ZK;
   const int S = zk ? Lq + R : Lq + 2 * R;
-  MMR_REQUIRE(in->query_ids && in->segment_ids && in->label_ids && in->feats, "mmr_forward: missing input pointer");
-  MMR_TRY(cast16(in->feats, h->f16, int64_t(B) * R * cfg.feat_dim, c.dt, c.st));
-  MMR_TRY(c.mark(K_ROW, 0));
+  const bool fused_in = zk && in->region_sum != nullptr;
+  MMR_REQUIRE(in->query_ids && in->segment_ids && (fused_in || (in->label_ids && in->feats)),
+              "mmr_forward: missing input pointer");
+  if (!fused_in) {
+    MMR_TRY(cast16(in->feats, h->f16, int64_t(B) * R * cfg.feat_dim, c.dt, c.st));
+    MMR_TRY(c.mark(K_ROW, 0));
+  }
   const int32_t* mask = nullptr;
   if (zk) {
-    MMR_REQUIRE(in->boxes && in->len_query && in->num_boxes && in->labels, "mmr_forward(zk): missing input pointer");
-    // feat = ReLU(f . Wc2 + bc2)  (model_triple.py:192-194)
-    MMR_TRY(c.G(h->f16, cfg.feat_dim, h->conv2, B * R, nullptr, nullptr, 0, h->tmp32, MMR_ACT_RELU));
-    MMR_TRY(zk_region_sum(h->tmp32, in->boxes, in->label_ids, h->tables, cfg.vocab, h->bc1, h->Wb, h->bb, h->t16,
-                          B * R, c.dt, c.st));
-    MMR_TRY(c.mark(K_ROW, 0));
+    MMR_REQUIRE(in->len_query && in->num_boxes && in->labels && (fused_in || in->boxes),
+                "mmr_forward(zk): missing input pointer");
+    if (fused_in) {
+      // caller already formed label + box + feat (pixelbert.BertModel's imgfeat argument)
+      MMR_TRY(cast16(in->region_sum, h->t16, int64_t(B) * R * H, c.dt, c.st));
+      MMR_TRY(c.mark(K_ROW, 0));
+    } else {
+      // feat = ReLU(f . Wc2 + bc2)  (model_triple.py:192-194)
+      MMR_TRY(c.G(h->f16, cfg.feat_dim, h->conv2, B * R, nullptr, nullptr, 0, h->tmp32, MMR_ACT_RELU));
+      MMR_TRY(zk_region_sum(h->tmp32, in->boxes, in->label_ids, h->tables, cfg.vocab, h->bc1, h->Wb, h->bb, h->t16,
+                            B * R, c.dt, c.st));
+      MMR_TRY(c.mark(K_ROW, 0));
+    }
     // region = (label + box + feat) . Wfe + bfe  (pixelbert.py:449-452)
     MMR_TRY(c.G(h->t16, H, h->featureemb, B * R, nullptr, nullptr, 0, h->tmp32, MMR_ACT_NONE));
     MMR_TRY(zk_embed(in->query_ids, in->segment_ids, h->tmp32, in->len_query, in->num_boxes, h->E, h->T, h->P,
@@ -614,7 +634,12 @@ static mmr_status forward_single_stream(Ctx& c, const mmr_inputs* in, int B, flo
   }
   if (h->keep_taps)
     MMR_CUDA_OK(cudaMemcpyAsync(h->emb_tap, h->x32, size_t(B) * S * H * 4, cudaMemcpyDeviceToDevice, c.st));
-  for (const Layer& L : h->layers) MMR_TRY(bert_layer(c, L, 0, B, S, mask));
+  for (size_t i = 0; i < h->layers.size(); ++i) {
+    MMR_TRY(bert_layer(c, h->layers[i], 0, B, S, mask));
+    if (h->layer_tap != nullptr && h->keep_taps >= 2)
+      MMR_CUDA_OK(cudaMemcpyAsync(h->layer_tap + i * size_t(h->rows_max) * H, h->x32, size_t(B) * S * H * 4,
+                                  cudaMemcpyDeviceToDevice, c.st));
+  }
   MMR_TRY(pooler(c, B, S));
   if (zk)
     MMR_TRY(zk_head(h->pooled32, h->am_wn, in->labels, B, probs, logits, c.st));
@@ -731,6 +756,7 @@ extern "C" void mmr_destroy(mmr_handle* h) {
   cudaSetDevice(h->device);
   if (h->weights.base) cudaFree(h->weights.base);
   if (h->work.base) cudaFree(h->work.base);
+  if (h->layer_tap) cudaFree(h->layer_tap);
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   delete h;
 }
@@ -759,7 +785,14 @@ extern "C" mmr_status mmr_forward(mmr_handle* h, const mmr_inputs* in, int B, fl
 
 extern "C" mmr_status mmr_set_debug_taps(mmr_handle* h, int enable) {
   MMR_REQUIRE(h, "mmr_set_debug_taps: null handle");
-  h->keep_taps = enable ? 1 : 0;
+  MMR_REQUIRE(enable >= 0 && enable <= 2, "mmr_set_debug_taps: enable must be 0, 1 or 2");
+  if (enable == 2 && h->layer_tap == nullptr) {
+    MMR_REQUIRE(h->cfg.model_kind != MMR_MODEL_LXMERT, "mmr_set_debug_taps: per-layer taps are for single-stream models");
+    MMR_CUDA_OK(cudaSetDevice(h->device));
+    MMR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->layer_tap),
+                           h->layers.size() * size_t(h->rows_max) * h->cfg.hidden * 4));
+  }
+  h->keep_taps = enable;
   return MMR_OK;
 }
 
@@ -779,6 +812,9 @@ extern "C" mmr_status mmr_get_activation(mmr_handle* h, int which, float* dst, i
     src = h->emb_tap;
   } else if (which == 1) {
     src = h->x32;
+  } else if (which >= 2 && which < 2 + int(h->layers.size()) && c.model_kind != MMR_MODEL_LXMERT) {
+    MMR_REQUIRE(h->keep_taps >= 2 && h->layer_tap, "mmr_get_activation: layer taps need mmr_set_debug_taps(h, 2)");
+    src = h->layer_tap + size_t(which - 2) * size_t(h->rows_max) * c.hidden;
   } else {
     return fail(MMR_ERR_INVALID, "mmr_get_activation: unknown tap %d", which);
   }

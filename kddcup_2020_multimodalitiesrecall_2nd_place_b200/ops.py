@@ -69,3 +69,18 @@ def cast16(x32, dtype=torch.bfloat16):
     out = torch.empty(x32.shape, dtype=dtype, device=x32.device)
     check(lib.mmr_cast16(x32.data_ptr(), out.data_ptr(), x32.numel(), dtype_code(dtype), _stream()))
     return out
+
+
+def gemm_layernorm(a16, w16, bias, x32, gamma, beta, eps=1e-12):
+    """x32 <- LN(a16 @ w16.T + bias + x32) * gamma + beta in place (fused kernel); returns (x16, x32)."""
+    lib = _lib.load()
+    M, K = a16.shape
+    assert w16.shape[0] == 768 and x32.shape == (M, 768) and x32.is_contiguous()
+    code = dtype_code(a16.dtype)
+    if not lib.mmr_gemm_layernorm_supported(M, K, code):
+        raise _lib.MmrError(f"fused GEMM+LayerNorm not available for M={M} K={K} on this device")
+    x16 = torch.empty((M, 768), dtype=a16.dtype, device=a16.device)
+    check(lib.mmr_gemm_layernorm(a16.data_ptr(), a16.stride(0), w16.data_ptr(), w16.stride(0), M, K, bias.data_ptr(),
+                                 x32.data_ptr(), 768, gamma.data_ptr(), beta.data_ptr(), eps, x16.data_ptr(), 768,
+                                 x32.data_ptr(), 768, code, _stream()))
+    return x16, x32

@@ -108,10 +108,18 @@ class MatchScorer:
         Returns probs [B,2] fp32 (the reference score is probs[:, 1])."""
         B = feeds["query_ids"].shape[0]
         inp = _lib.MmrInputs()
+        fused = feeds.get("region_sum") if self.cfg.kind == ZK else None
         for name in self.spec:
+            if fused is not None and name in ("feats", "boxes", "label_ids"):
+                continue
             t = feeds[name]
             self._check_feed(name, t, B)
             setattr(inp, name, t.data_ptr())
+        if fused is not None:
+            if fused.dtype != torch.float32 or tuple(fused.shape) != (B, self.cfg.nbox, self.cfg.hidden) \
+                    or not fused.is_contiguous():
+                raise ValueError("feed 'region_sum': need contiguous float32 [B, nbox, hidden]")
+            inp.region_sum = fused.data_ptr()
         if probs_out is None:
             probs_out = torch.empty((B, 2), dtype=torch.float32, device=self.device)
         _lib.check(self.lib.mmr_forward(self._h, C.byref(inp), B, probs_out.data_ptr(),
@@ -136,11 +144,13 @@ class MatchScorer:
             raise _lib.MmrError("mmr_get_profile failed")
         return [(int(kinds[i]), float(ms[i]), float(fl[i])) for i in range(n)]
 
-    def set_debug_taps(self, on: bool):
-        _lib.check(self.lib.mmr_set_debug_taps(self._h, int(on)))
+    def set_debug_taps(self, level):
+        """0 off, 1 keep the embedding output, 2 also keep every encoder layer's output (single-stream models)."""
+        _lib.check(self.lib.mmr_set_debug_taps(self._h, int(level)))
 
     def activation(self, which: int, batch: int) -> torch.Tensor:
-        """Parity tap after the last forward: 0 = embedding output, 1 = final encoder output; [rows, hidden]."""
+        """Parity tap after the last forward: 0 = embedding output, 1 = final encoder output, 2 + i = encoder layer i;
+        [rows, hidden]."""
         cfg = self.cfg
         rows = batch * (cfg.lq + (2 if cfg.kind == LDS else 1) * cfg.nbox)
         out = torch.empty((rows, cfg.hidden), dtype=torch.float32, device=self.device)

@@ -139,3 +139,29 @@ def test_cast16_is_round_to_nearest_even():
     x = torch.randn(36 * 7, 2048, device="cuda")
     for dt in (torch.float16, torch.bfloat16):
         assert torch.equal(ops.cast16(x, dt), x.to(dt))
+
+
+@pytest.mark.parametrize("M,K", [(17408, 768), (17408, 3072), (8192, 768), (300, 768), (1000, 3072), (129, 768)])
+def test_fused_gemm_layernorm(M, K):
+    """One kernel = dense + bias + residual + LayerNorm (cluster of three CTA pairs, DSMEM statistics exchange)
+    against the unfused fp32 reference; in place on the residual stream, ragged M included."""
+    from kddcup_2020_multimodalitiesrecall_2nd_place_b200 import ops, _lib
+    lib = _lib.load()
+    if not lib.mmr_gemm_layernorm_supported(M, K, _lib.DT_FP16):
+        pytest.skip("device cannot co-schedule a 6-CTA cluster with this kernel's shared memory")
+    torch.manual_seed(M + K)
+    a = torch.randn(M, K, device="cuda").half()
+    w = (torch.randn(768, K, device="cuda") * 0.03).half()
+    b = torch.randn(768, device="cuda") * 0.1
+    x = torch.randn(M, 768, device="cuda") * 2 + 0.3
+    g = torch.rand(768, device="cuda") + 0.5
+    be = torch.randn(768, device="cuda") * 0.1
+    ref = F.layer_norm(a.float() @ w.float().t() + b + x, (768,), g, be, 1e-12)
+    x16, x32 = ops.gemm_layernorm(a, w, b, x, g, be)
+    torch.cuda.synchronize()
+    assert x32.data_ptr() == x.data_ptr()
+    assert _rel(x32, ref) < 1e-5
+    assert _rel(x16, ref) < 6e-4
+    # every row is normalised: mean ~ beta-weighted, but the pre-affine statistics must be exact
+    z = (x32 - be) / g
+    assert z.mean(1).abs().max().item() < 1e-4 and (z.var(1, unbiased=False) - 1).abs().max().item() < 1e-3

@@ -65,7 +65,63 @@ def child():
               f"(cuBLAS plain fp16 matmul {ms2*1e3:7.1f} us {2*M*N*K/ms2/1e9:7.1f} TFLOP/s)", flush=True)
 
 
+def child_ln():
+    import torch
+    import torch.nn.functional as F
+    from kddcup_2020_multimodalitiesrecall_2nd_place_b200 import ops
+    torch.manual_seed(0)
+    for (M, K) in [(300, 768), (17408, 768), (17408, 3072), (26624, 768), (8192, 3072)]:
+        a = torch.randn(M, K, device="cuda").half()
+        w = (torch.randn(768, K, device="cuda") * 0.03).half()
+        b = torch.randn(768, device="cuda") * 0.1
+        x = torch.randn(M, 768, device="cuda")
+        g = torch.rand(768, device="cuda") + 0.5
+        be = torch.randn(768, device="cuda") * 0.1
+        ref = F.layer_norm(a.float() @ w.float().t() + b + x, (768,), g, be, 1e-12)
+        x16, x32 = ops.gemm_layernorm(a, w, b, x.clone(), g, be)
+        torch.cuda.synchronize()
+        e32 = ((x32 - ref).abs().max() / ref.abs().max()).item()
+        print(f"fused-LN check M={M} K={K}: rel32={e32:.2e}", flush=True)
+        assert e32 < 1e-5
+        xs = x.clone()
+        for _ in range(3):
+            ops.gemm_layernorm(a, w, b, xs, g, be)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 20
+        e0.record()
+        for _ in range(n):
+            ops.gemm_layernorm(a, w, b, xs, g, be)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        # unfused: GEMM(+residual, fp32 out) then LayerNorm
+        for _ in range(3):
+            _, y = ops.gemm(a, w, b, xs, want16=False, want32=True)
+            ops.layernorm(y, g, be, dtype=torch.float16)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            _, y = ops.gemm(a, w, b, xs, want16=False, want32=True)
+            ops.layernorm(y, g, be, dtype=torch.float16)
+        e1.record()
+        torch.cuda.synchronize()
+        ms2 = e0.elapsed_time(e1) / n
+        print(f"fused-LN time M={M} K={K}: {ms*1e3:7.1f} us {2*M*768*K/ms/1e9:7.1f} TFLOP/s   (GEMM+residual then LN: "
+              f"{ms2*1e3:7.1f} us)", flush=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "child_ln":
+        child_ln()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "ln":
+        try:
+            r = subprocess.run([sys.executable, __file__, "child_ln"], capture_output=True, text=True, timeout=300)
+            print(r.stdout + (("\n[stderr]\n" + r.stderr[-3000:]) if r.returncode else ""), f"rc={r.returncode}", flush=True)
+        except subprocess.TimeoutExpired as e:
+            print("TIMEOUT", (e.stdout or b"")[-3000:], flush=True)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "child":
         child()
         sys.exit(0)
