@@ -88,7 +88,8 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
   // at fp32 rounding level) instead of erff(): ~12 instructions with one ex2 and one rcp on the SFU, which keeps the
   // FFN epilogue inside the time of its tile's MMAs (erff() made the LXMERT FFN-in GEMM epilogue-bound).
   const float z = fabsf(x) * 0.7071067811865475f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));   // MUFU.RCP (1 ulp), not the IEEE sequence
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);

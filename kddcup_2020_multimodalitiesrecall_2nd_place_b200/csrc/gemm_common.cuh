@@ -130,11 +130,18 @@ __device__ __forceinline__ void epilogue_warp(const GemmParams& p, uint32_t tadd
 // 2-D tensor map over a row-major 16-bit matrix [rows, cols] with row stride ld (elements); box = 64 x box_rows,
 // 128-byte swizzle (must match umma_desc_k_sw128).
 mmr_status make_tmap_2d(void* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int dtype);
+mmr_status make_tmap_ex(void* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int elem_kind,
+                        int box_cols, int box_rows, int swizzle_bytes);
 int sm_count();
 
 // CTA-pair kernel (gemm2_sm100.cu): used when N is a multiple of 256 and M spans more than one 128-row block.
 bool gemm_pair_eligible(int M, int N, int K);
 mmr_status gemm_pair(const void* A16, int64_t lda, const void* W16, int64_t ldw, const GemmParams& p, int act,
                      int dtype, cudaStream_t stream);
+
+// 16-bit-output variant with a TMA-store epilogue and a split tail wave (gemm16_sm100.cu).
+bool gemm_pair16_eligible(int M, int N, int K, const float* residual, const void* out16, const float* out32);
+mmr_status gemm_pair16(const void* A16, int64_t lda, const void* W16, int64_t ldw, int M, int N, int K,
+                       const float* bias, void* out16, int64_t ldo16, int act, int dtype, cudaStream_t stream);
 
 }  // namespace mmr

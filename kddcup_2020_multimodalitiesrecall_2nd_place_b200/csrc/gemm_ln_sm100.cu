@@ -2,100 +2,84 @@
 //
 // Replaces the "dense -> dropout(identity) -> layer_norm(out + input)" tails of the reference blocks
 // (imagebert_zk/pixelbert.py:960-966 and 977-983; lxmert/src/lxrt/modeling.py:355-366 and 409-420), which the first
-// version of this repo ran as a GEMM that wrote y (fp32) and a LayerNorm kernel that re-read it: 107 MB of avoidable
-// HBM traffic and one launch per LayerNorm, 24 times per 12-layer forward.
+// version of this repo ran as a GEMM that wrote y (fp32) and a LayerNorm kernel that re-read it: 132 MB of avoidable
+// traffic and one launch per LayerNorm, 24 times per 12-layer forward.
 //
-// A LayerNorm row spans N = 768 = 3 tiles of 256 columns, more fp32 accumulator columns than one SM's TMEM holds
-// (512).  So a CLUSTER OF 6 CTAs = 3 CTA pairs owns one 256-row block: pair p computes columns [256p, 256p+256) with
-// tcgen05.mma.cta_group::2 exactly like gemm2_sm100.cu, and the epilogues meet once per tile:
-//   pass 1   y = acc + bias + residual, written back into the TMEM accumulator (tcgen05.st); per-thread row sums
-//   pass 1b  centred second moment of this thread's 128 columns (re-reads TMEM; numerically a two-pass variance)
-//   exchange each warp publishes (mean_i, M2_i) of its 32 rows to the 3 CTAs holding the same rows, through
-//            distributed shared memory, and arrives on their "stats" mbarriers (release/acquire at cluster scope)
-//   combine  Chan's parallel formula over the 6 partials of a row -> mean, rstd
-//   pass 2   normalise from TMEM, affine, park in the warp's smem stage, store fp32 + 16-bit rows coalesced
-// Residual rows are fetched coalesced, one chunk ahead (the first chunk even before the accumulator is complete),
-// and transposed through the same per-warp smem stage so that every thread gets its own row.
+// A LayerNorm row spans N = 768 = 3 tiles of 256 fp32 accumulator columns, more than one SM's TMEM holds twice over,
+// so three CTA pairs (a GROUP: pairs 3g, 3g+1, 3g+2 of the grid) share each 256-row block: pair n computes columns
+// [256 n, 256 n + 256) with the pair_pipeline.cuh main loop, and the epilogues meet once per block:
+//   pass 1    y = acc + bias + residual, parked back into the TMEM accumulator (tcgen05.st); shifted sums per thread
+//             (one thread = one row of its warp's 128 columns); residual chunks arrive by TMA into a 2-slot ring
+//   exchange  every warp publishes (mean_i, M2_i) of its 32 rows x 128 columns to a small global table and bumps the
+//             counter of its (block, 32-row quarter); it then waits for the 6 partials of its rows (3 column tiles x
+//             2 halves).  The wait is on warps that run the SAME step on neighbouring SMs at the same time; the MMAs
+//             of the next tile proceed meanwhile in the other accumulator.
+//   combine   Chan's parallel formula over the 6 partials -> mean, rstd
+//   pass 2    normalise from TMEM, affine, write the fp32 rows and their 16-bit mirror into swizzled stages, TMA-store
+// The groups are plain CTA pairs, not a 6-CTA cluster (the first version of this file): a 6-CTA cluster fits only 22
+// times on the 148 SMs (GPC granularity) which turns 68 row blocks into 4 waves; 24 groups of pairs make it 3.
+// Requirement: every CTA of the grid is resident at once (the grid never exceeds the co-residency the occupancy API
+// reports, and the spin is bounded: a violation traps instead of hanging).
 #include <cuda.h>
 
 #include <cstdlib>
 
-#include "gemm_common.cuh"
 #include "kernels.cuh"
+#include "pair_pipeline.cuh"
 
 namespace mmr {
 
 constexpr int kLnN = 768;
-constexpr int kLnPairs = kLnN / kBN;            // 3 CTA pairs per cluster
-constexpr int kLnCluster = 2 * kLnPairs;        // 6 CTAs
-constexpr int kLnBM = 256;
-constexpr int kLnHalfM = 128;
-constexpr int kLnHalfN = kBN / 2;
-constexpr int kLnStages = 5;
-constexpr int kLnSlots = 2 * kLnPairs;          // partial statistics per row: 3 n-tiles x 2 column halves
-constexpr uint32_t kLnABytes = kLnHalfM * kBK * 2;
-constexpr uint32_t kLnBBytes = kLnHalfN * kBK * 2;
-constexpr uint32_t kLnStageBytes = kLnABytes + kLnBBytes;
-constexpr size_t kLnPartBytes = size_t(2) * kLnSlots * kLnHalfM * sizeof(float2);   // double-buffered, 12 KB
-constexpr size_t kLnSmemBytes = 1024 + size_t(kLnStages) * kLnStageBytes + 256 + kEpiSmemBytes + kLnPartBytes;
+constexpr int kLnTiles = kLnN / kBN;            // 3 column tiles = 3 pairs per group
+constexpr int kLnStages = 4;
+constexpr int kLnSlots = 2 * kLnTiles;          // partial statistics per row: 3 column tiles x 2 halves
+constexpr int kLnWarpBytes = 2 * 4096 + 2 * 2048;   // per epilogue warp: two fp32 slots + two 16-bit stages
+constexpr size_t kLnSmemBytes = 1024 + PairRing<kLnStages>::kOperandBytes + size_t(kEpiWarps) * kLnWarpBytes + 512;
 
 struct GemmLnParams {
   int M, K;
   const float* bias;      // [768]
-  const float* residual;  // [M, ldr] (may alias out32)
-  int64_t ldr;
   const float* gamma;     // [768]
   const float* beta;      // [768]
   float eps;
-  void* out16;            // [M, ldo16] or null
-  int64_t ldo16;
-  float* out32;           // [M, ldo32] or null
-  int64_t ldo32;
+  float2* stats;          // [m_tiles][6][256]  (mean_i, M2_i) partials
+  uint32_t* counters;     // [m_tiles][2][4] arrivals per (row block, CTA rank, 32-row quarter); zero between launches
+  uint32_t* done;         // CTAs finished (the last one re-zeroes the counters)
   uint32_t idesc_fmt;
 };
 
 template <class E16>
-__global__ void __cluster_dims__(kLnCluster, 1, 1) __launch_bounds__(kGemmThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-               const GemmLnParams p) {
+               const __grid_constant__ CUtensorMap tmap_r, const __grid_constant__ CUtensorMap tmap_o32,
+               const __grid_constant__ CUtensorMap tmap_o16, const GemmLnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + size_t(kLnStages) * kLnABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(kLnStages) * kLnStageBytes);
-  uint64_t* full_bar = bars;                    // [stages]  used in the pair leader
-  uint64_t* empty_bar = bars + kLnStages;       // [stages]
-  uint64_t* tfull_bar = bars + 2 * kLnStages;   // [2]
-  uint64_t* tempty_bar = tfull_bar + 2;         // [2]       used in the pair leader
-  uint64_t* stats_bar = tempty_bar + 2;         // [2][4]    per 32-row quarter: 6 warp arrivals (2 local, 4 remote) per tile
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stats_bar + 8);
-  float* epi_stage = reinterpret_cast<float*>(smem + size_t(kLnStages) * kLnStageBytes + 256);
-  float2* part = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(epi_stage) + kEpiSmemBytes);  // [2][6][128]
+  uint8_t* epi = smem + PairRing<kLnStages>::kOperandBytes;                       // 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi + size_t(kEpiWarps) * kLnWarpBytes);
+  PairRing<kLnStages> ring;
+  ring.carve(smem, bars);
+  uint64_t* res_bar = bars + PairRing<kLnStages>::kNumBars;    // [8 warps][2 slots] residual chunk landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * kEpiWarps);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank6 = cluster_ctarank();
-  const uint32_t r = rank6 & 1u;                 // which 128-row half of the block this CTA owns
-  const uint32_t n_tile = rank6 >> 1;            // which 256-column tile this CTA's pair owns
-  const uint32_t leader = rank6 & ~1u;           // cluster rank of this pair's MMA-issuing CTA
-  const int cluster_id = blockIdx.x / kLnCluster;
-  const int n_clusters = gridDim.x / kLnCluster;
-
-  const int m_tiles = (p.M + kLnBM - 1) / kLnBM;
+  const uint32_t rank = cluster_ctarank();        // which 128-row half of the block this CTA owns
+  const int pair = blockIdx.x >> 1;
+  const int n_groups = (gridDim.x >> 1) / kLnTiles;
+  const int group = pair / kLnTiles;
+  const int n_tile = pair % kLnTiles;             // which 256-column tile this pair owns
+  const int m_tiles = (p.M + kPairRows - 1) / kPairRows;
   const int k_blocks = p.K / kBK;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_w);
-    for (int s = 0; s < kLnStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 2 * kEpiWarps);
-      for (int q = 0; q < 4; ++q) mbar_init(&stats_bar[s * 4 + q], kLnSlots);
-    }
+    tma_prefetch_desc(&tmap_r);
+    tma_prefetch_desc(&tmap_o32);
+    tma_prefetch_desc(&tmap_o16);
+    ring.init(2 * kEpiWarps);
+    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -109,50 +93,24 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const int w_row = int(n_tile) * kBN + int(r) * kLnHalfN;
-      for (int tile = cluster_id; tile < m_tiles; tile += n_clusters) {
-        const int a_row = tile * kLnBM + int(r) * kLnHalfM;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
-          const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), leader);
-          if (r == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kLnStageBytes);
-          tma_load_2d_2sm(smem_a + size_t(stage) * kLnABytes, &tmap_a, full_leader, kb * kBK, a_row);
-          tma_load_2d_2sm(smem_b + size_t(stage) * kLnBBytes, &tmap_w, full_leader, kb * kBK, w_row);
-          if (++stage == kLnStages) { stage = 0; phase ^= 1u; }
-        }
-      }
+      RingPos pos;
+      const int w_row = n_tile * kBN + int(rank) * (kBN / 2);
+      for (int m_blk = group; m_blk < m_tiles; m_blk += n_groups)
+        pair_produce_tile<kLnStages>(ring, pos, &tmap_a, &tmap_w, m_blk * kPairRows + int(rank) * kCtaRows, w_row,
+                                     kBN / 2, k_blocks, rank, 0);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (pair leader, one thread) =====================
-    if (r == 0 && lane == 0) {
-      const uint32_t idesc = umma_idesc_f16(p.idesc_fmt, kLnBM, kBN);
-      const uint16_t pair_mask = uint16_t(0b11u << leader);
-      int stage = 0;
-      uint32_t phase = 0;
+    if (rank == 0 && lane == 0) {
+      RingPos pos;
+      const uint32_t idesc = umma_idesc_f16(p.idesc_fmt, kPairRows, kBN);
       int it = 0;
-      for (int tile = cluster_id; tile < m_tiles; tile += n_clusters, ++it) {
+      for (int m_blk = group; m_blk < m_tiles; m_blk += n_groups, ++it) {
         const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1u;
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + uint32_t(acc) * kBN;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint64_t a_desc = umma_desc_k_sw128(smem_u32(smem_a + size_t(stage) * kLnABytes));
-          const uint64_t b_desc = umma_desc_k_sw128(smem_u32(smem_b + size_t(stage) * kLnBBytes));
-#pragma unroll
-          for (int k = 0; k < kBK / kUmmaK; ++k) {
-            umma_f16_2sm(tmem_d, a_desc + uint64_t(2 * k), b_desc + uint64_t(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-          }
-          umma_commit_2sm_mc(&empty_bar[stage], pair_mask);
-          if (++stage == kLnStages) { stage = 0; phase ^= 1u; }
-        }
-        umma_commit_2sm_mc(&tfull_bar[acc], pair_mask);
+        pair_mma_tile<kLnStages>(ring, pos, tmem_base + uint32_t(acc) * kBN, idesc, k_blocks, acc, (it >> 1) & 1u,
+                                 0b11);
       }
     }
   } else {
@@ -160,153 +118,155 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int ew = warp - 2;
     const int quarter = warp & 3;
     const int half = ew >> 2;
-    float* stage_w = epi_stage + ew * kEpiStageFloats;
-    const int slot = int(n_tile) * 2 + half;
-    const int row_in_cta = quarter * 32 + lane;
-    const int col_base = int(n_tile) * kBN + half * 128;    // first of this warp's 128 columns
-    const int rl_sub = lane >> 3, c4 = lane & 7;             // row-major (coalesced) mapping of phase-2 style accesses
+    uint8_t* wbuf = epi + size_t(ew) * kLnWarpBytes;
+    // wbuf + 4096 s       : fp32 slot s    [32 rows x 32 cols], 128-byte swizzle
+    // wbuf + 8192 + 2048 s: 16-bit stage s [32 rows x 32 cols], 64-byte swizzle
+    uint64_t* rfull = res_bar + 2 * ew;
+    const uint32_t tempty_leader0 = mapa_u32(smem_u32(&ring.tempty[0]), 0);
+    const uint32_t tempty_leader1 = mapa_u32(smem_u32(&ring.tempty[1]), 0);
+    const int col_w = n_tile * kBN + half * 128;            // first of this warp's 128 columns
+    const int row_in_blk = int(rank) * kCtaRows + quarter * 32;
+    const uint32_t sw128 = uint32_t(lane & 7), sw64 = uint32_t((lane >> 1) & 3);
+    uint32_t rph = 0;                                       // parity bits of the two residual barriers
     int it = 0;
-    for (int tile = cluster_id; tile < m_tiles; tile += n_clusters, ++it) {
+    for (int m_blk = group; m_blk < m_tiles; m_blk += n_groups, ++it) {
       const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1u;
-      const int row0 = tile * kLnBM + int(r) * kLnHalfM + quarter * 32;
+      const int row0 = m_blk * kPairRows + row_in_blk;
       const uint32_t taddr = tmem_base + uint32_t(acc) * kBN + (uint32_t(quarter * 32) << 16) + uint32_t(half * 128);
 
-      // residual rows of chunk 0, in flight while the MMAs of this tile finish
-      float4 res[8];
+      // residual chunks 0 and 1 -> slots (the previous block's stores must have finished reading them)
+      if (lane == 0) {
+        bulk_wait_read<0>();
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int grow = row0 + i * 4 + rl_sub;
-        res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (grow < p.M) res[i] = *reinterpret_cast<const float4*>(p.residual + int64_t(grow) * p.ldr + col_base + 4 * c4);
+        for (int s = 0; s < 2; ++s) {
+          mbar_arrive_expect_tx(&rfull[s], 4096);
+          tma_load_2d(wbuf + 4096 * s, &tmap_r, &rfull[s], col_w + 32 * s, row0);
+        }
       }
-      mbar_wait(&tfull_bar[acc], acc_phase);
+      mbar_wait(&ring.tfull[acc], (it >> 1) & 1u);
       tc_fence_after();
 
-      // ---- pass 1: y = acc + bias + residual -> back into TMEM; row sum
-      float sum = 0.f;
+      // ---- pass 1: y = acc + bias + residual -> back into TMEM; shifted sums (shift = this thread's first y)
+      float shift = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
+        const int s = c & 1;
+        uint8_t* slot_s = wbuf + 4096 * s;
+        float4 bb[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rl = i * 4 + rl_sub;
-          *reinterpret_cast<float4*>(stage_w + rl * 32 + ((c4 ^ (rl & 7)) << 2)) = res[i];
-        }
-        __syncwarp();
-        if (c < 3) {   // next chunk's residual rows
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int grow = row0 + i * 4 + rl_sub;
-            res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (grow < p.M)
-              res[i] = *reinterpret_cast<const float4*>(p.residual + int64_t(grow) * p.ldr + col_base + (c + 1) * 32 + 4 * c4);
-          }
-        }
+        for (int j = 0; j < 8; ++j) bb[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col_w + c * 32 + 4 * j));
+        mbar_wait(&rfull[s], (rph >> s) & 1u);
+        rph ^= 1u << s;
         uint32_t v[32];
         tmem_ld_32x32(taddr + uint32_t(c * 32), v);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col_base + c * 32 + 4 * j));
-          const float4 x = *reinterpret_cast<const float4*>(stage_w + lane * 32 + ((j ^ (lane & 7)) << 2));
-          const float y0 = __uint_as_float(v[4 * j]) + b.x + x.x, y1 = __uint_as_float(v[4 * j + 1]) + b.y + x.y;
-          const float y2 = __uint_as_float(v[4 * j + 2]) + b.z + x.z, y3 = __uint_as_float(v[4 * j + 3]) + b.w + x.w;
-          sum += (y0 + y1) + (y2 + y3);
+          const float4 x = *reinterpret_cast<const float4*>(slot_s + lane * 128 + ((uint32_t(j) ^ sw128) << 4));
+          const float y0 = __uint_as_float(v[4 * j]) + bb[j].x + x.x, y1 = __uint_as_float(v[4 * j + 1]) + bb[j].y + x.y;
+          const float y2 = __uint_as_float(v[4 * j + 2]) + bb[j].z + x.z, y3 = __uint_as_float(v[4 * j + 3]) + bb[j].w + x.w;
+          if (c == 0 && j == 0) shift = y0;
+          const float d0 = y0 - shift, d1 = y1 - shift, d2 = y2 - shift, d3 = y3 - shift;
+          s1 += (d0 + d1) + (d2 + d3);
+          s2 = fmaf(d0, d0, s2); s2 = fmaf(d1, d1, s2); s2 = fmaf(d2, d2, s2); s2 = fmaf(d3, d3, s2);
           v[4 * j] = __float_as_uint(y0); v[4 * j + 1] = __float_as_uint(y1);
           v[4 * j + 2] = __float_as_uint(y2); v[4 * j + 3] = __float_as_uint(y3);
         }
         tmem_st_32x32(taddr + uint32_t(c * 32), v);
-        __syncwarp();   // every lane has read its stage row before the next chunk overwrites the stage
+        __syncwarp();   // every lane has read its slot row
+        if (lane == 0 && c < 2) {
+          mbar_arrive_expect_tx(&rfull[s], 4096);
+          tma_load_2d(slot_s, &tmap_r, &rfull[s], col_w + 32 * (c + 2), row0);
+        }
       }
       tmem_st_wait();
 
-      // ---- pass 1b: centred second moment of this thread's 128 columns
-      const float mean_i = sum * (1.0f / 128.0f);
-      float m2 = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + uint32_t(c * 32), v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float d = __uint_as_float(v[j]) - mean_i;
-          m2 = fmaf(d, d, m2);
-        }
-      }
-
-      // ---- exchange: publish (mean_i, M2_i) to the three CTAs that hold these rows (own rank parity r)
-      const int buf = it & 1;
-      const uint32_t my_slot_addr = smem_u32(part + (size_t(buf) * kLnSlots + slot) * kLnHalfM + row_in_cta);
-#pragma unroll
-      for (int t = 0; t < kLnPairs; ++t) st_cluster_f32x2(mapa_u32(my_slot_addr, uint32_t(2 * t) + r), mean_i, m2);
-      asm volatile("fence.acq_rel.cluster;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) {
-#pragma unroll
-        for (int t = 0; t < kLnPairs; ++t)
-          mbar_arrive_cluster(mapa_u32(smem_u32(&stats_bar[buf * 4 + quarter]), uint32_t(2 * t) + r));
-      }
-      mbar_wait_cluster(&stats_bar[buf * 4 + quarter], acc_phase);
-
-      // ---- combine the 6 partials of this row (equal counts: Chan et al.)
-      float means[kLnSlots], mean = 0.f, m2_tot = 0.f;
-#pragma unroll
-      for (int s = 0; s < kLnSlots; ++s) {
-        const float2 q = part[(size_t(buf) * kLnSlots + s) * kLnHalfM + row_in_cta];
-        means[s] = q.x;
-        mean += q.x;
-        m2_tot += q.y;
-      }
-      mean *= (1.0f / kLnSlots);
-#pragma unroll
-      for (int s = 0; s < kLnSlots; ++s) {
-        const float d = means[s] - mean;
-        m2_tot = fmaf(128.0f * d, d, m2_tot);
-      }
-      const float rstd = rsqrtf(m2_tot * (1.0f / kLnN) + p.eps);
-
-      // ---- pass 2: normalise, affine, coalesced stores
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + uint32_t(c * 32), v);
-        tmem_ld_wait();
-        const int col0 = col_base + c * 32;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + col0 + 4 * j));
-          const float4 b = __ldg(reinterpret_cast<const float4*>(p.beta + col0 + 4 * j));
-          float4 y;
-          y.x = (__uint_as_float(v[4 * j]) - mean) * rstd * g.x + b.x;
-          y.y = (__uint_as_float(v[4 * j + 1]) - mean) * rstd * g.y + b.y;
-          y.z = (__uint_as_float(v[4 * j + 2]) - mean) * rstd * g.z + b.z;
-          y.w = (__uint_as_float(v[4 * j + 3]) - mean) * rstd * g.w + b.w;
-          *reinterpret_cast<float4*>(stage_w + lane * 32 + ((j ^ (lane & 7)) << 2)) = y;
-        }
+      // ---- exchange: publish (mean_i, M2_i) of this thread's 128 columns, wait for the 6 partials of its row
+      float mean, rstd;
+      {
+        const float mean_i = shift + s1 * (1.0f / 128.0f);
+        const float m2_i = fmaxf(s2 - s1 * s1 * (1.0f / 128.0f), 0.f);
+        float2* tab = p.stats + size_t(m_blk) * kLnSlots * kPairRows + row_in_blk + lane;
+        tab[size_t(n_tile * 2 + half) * kPairRows] = make_float2(mean_i, m2_i);
+        __threadfence();
         __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rl = i * 4 + rl_sub;
-          const float4 x = *reinterpret_cast<const float4*>(stage_w + rl * 32 + ((c4 ^ (rl & 7)) << 2));
-          const int grow = row0 + rl;
-          if (grow < p.M) {
-            const int gcol = col0 + 4 * c4;
-            if (p.out32 != nullptr) *reinterpret_cast<float4*>(p.out32 + int64_t(grow) * p.ldo32 + gcol) = x;
-            if (p.out16 != nullptr) {
-              uint2 q;
-              q.x = E16::pack(x.x, x.y); q.y = E16::pack(x.z, x.w);
-              *reinterpret_cast<uint2*>(reinterpret_cast<typename E16::T*>(p.out16) + int64_t(grow) * p.ldo16 + gcol) = q;
-            }
+        uint32_t* ctr = p.counters + (m_blk * 2 + int(rank)) * 4 + quarter;
+        if (lane == 0) {
+          atomicAdd(ctr, 1u);
+          uint32_t spins = 0;
+          while (ld_acquire_gpu_u32(ctr) < uint32_t(kLnSlots)) {
+            if (++spins > MMR_SPIN_LIMIT) __trap();
           }
         }
         __syncwarp();
+        float means[kLnSlots], m2_tot = 0.f;
+        mean = 0.f;
+#pragma unroll
+        for (int s = 0; s < kLnSlots; ++s) {
+          const float2 q = __ldcg(tab + size_t(s) * kPairRows);
+          means[s] = q.x;
+          mean += q.x;
+          m2_tot += q.y;
+        }
+        mean *= (1.0f / kLnSlots);
+#pragma unroll
+        for (int s = 0; s < kLnSlots; ++s) {
+          const float d = means[s] - mean;
+          m2_tot = fmaf(128.0f * d, d, m2_tot);
+        }
+        rstd = rsqrtf(m2_tot * (1.0f / kLnN) + p.eps);
       }
-      // accumulator drained -> back to the pair leader's MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), leader));
+
+      // ---- pass 2: normalise from TMEM, affine, swizzled stages, TMA stores
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int s = c & 1;
+        uint8_t* slot_s = wbuf + 4096 * s;
+        uint8_t* o16_s = wbuf + 8192 + 2048 * s;
+        const int col0 = col_w + c * 32;
+        float4 gg[8], be[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          gg[j] = __ldg(reinterpret_cast<const float4*>(p.gamma + col0 + 4 * j));
+          be[j] = __ldg(reinterpret_cast<const float4*>(p.beta + col0 + 4 * j));
+        }
+        if (lane == 0) bulk_wait_read<1>();   // the stores issued two chunks ago have read this slot and stage
+        __syncwarp();
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + uint32_t(c * 32), v);
+        tmem_ld_wait();
+        if (c == 3) {
+          // accumulator drained -> back to the pair leader's MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster_relaxed(acc ? tempty_leader1 : tempty_leader0);
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 y;
+          y.x = (__uint_as_float(v[4 * j]) - mean) * rstd * gg[j].x + be[j].x;
+          y.y = (__uint_as_float(v[4 * j + 1]) - mean) * rstd * gg[j].y + be[j].y;
+          y.z = (__uint_as_float(v[4 * j + 2]) - mean) * rstd * gg[j].z + be[j].z;
+          y.w = (__uint_as_float(v[4 * j + 3]) - mean) * rstd * gg[j].w + be[j].w;
+          *reinterpret_cast<float4*>(slot_s + lane * 128 + ((uint32_t(j) ^ sw128) << 4)) = y;
+          pk[2 * j] = E16::pack(y.x, y.y);
+          pk[2 * j + 1] = E16::pack(y.z, y.w);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(o16_s + lane * 64 + ((uint32_t(q) ^ sw64) << 4)) =
+              make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(slot_s, &tmap_o32, col0, row0);
+          tma_store_2d(o16_s, &tmap_o16, col0, row0);
+          bulk_commit();
+        }
+      }
     }
+    if (lane == 0) bulk_wait<0>();
   }
 
   tc_fence_before();
@@ -316,11 +276,49 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tc_fence_after();
     tmem_dealloc_2sm(tmem_base, kTmemCols);
   }
+  // The last CTA to finish zeroes the arrival counters for the next launch (nobody can still be polling them).
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(p.done, 1u) == gridDim.x - 1) {
+      for (int i = 0; i < m_tiles * 8; ++i) p.counters[i] = 0;
+      *p.done = 0;
+      __threadfence();
+    }
+  }
 }
 
-// Largest number of co-resident 6-CTA clusters (0 when the device cannot place one): queried once.
+// ------------------------------------------------------------------------------------------------ host side
+// Exchange table + counters, one per device, grown on demand (mmr_create reserves it for max_batch so that no
+// allocation happens inside mmr_forward).  One fused GEMM+LN may be in flight per device at a time.
+struct LnWorkspace {
+  float2* stats = nullptr;
+  uint32_t* counters = nullptr;
+  int m_tiles = 0;
+};
+static LnWorkspace g_ln_ws[16];
+
+mmr_status gemm_ln_reserve(int M) {
+  int dev = 0;
+  MMR_CUDA_OK(cudaGetDevice(&dev));
+  MMR_REQUIRE(dev >= 0 && dev < 16, "gemm_ln: device index %d out of range", dev);
+  LnWorkspace& ws = g_ln_ws[dev];
+  const int m_tiles = (M + kPairRows - 1) / kPairRows;
+  if (m_tiles <= ws.m_tiles) return MMR_OK;
+  MMR_CUDA_OK(cudaDeviceSynchronize());   // a kernel may still use the old table
+  if (ws.stats) cudaFree(ws.stats);
+  if (ws.counters) cudaFree(ws.counters);
+  ws = LnWorkspace();
+  MMR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&ws.stats), size_t(m_tiles) * kLnSlots * kPairRows * sizeof(float2)));
+  MMR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&ws.counters), (size_t(m_tiles) * 8 + 1) * sizeof(uint32_t)));
+  MMR_CUDA_OK(cudaMemset(ws.counters, 0, (size_t(m_tiles) * 8 + 1) * sizeof(uint32_t)));
+  MMR_CUDA_OK(cudaDeviceSynchronize());
+  ws.m_tiles = m_tiles;
+  return MMR_OK;
+}
+
+// Largest number of co-resident CTA pairs of this kernel (0 when the device cannot place one): queried once.
 template <class E16>
-static int ln_max_clusters() {
+static int ln_max_pairs() {
   static int cached = -1;
   if (cached >= 0) return cached;
   auto kern = gemm_ln_kernel<E16>;
@@ -329,12 +327,12 @@ static int ln_max_clusters() {
     return cached = 0;
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(kLnCluster * 64, 1, 1);
+  cfg.gridDim = dim3(2 * 74, 1, 1);
   cfg.blockDim = dim3(kGemmThreads, 1, 1);
   cfg.dynamicSmemBytes = kLnSmemBytes;
   cudaLaunchAttribute attr;
   attr.id = cudaLaunchAttributeClusterDimension;
-  attr.val.clusterDim.x = kLnCluster;
+  attr.val.clusterDim.x = 2;
   attr.val.clusterDim.y = 1;
   attr.val.clusterDim.z = 1;
   cfg.attrs = &attr;
@@ -352,16 +350,17 @@ bool gemm_ln_eligible(int M, int N, int K, int dtype) {
     const char* e = getenv("MMR_GEMM_LN");   // MMR_GEMM_LN=0 falls back to GEMM + separate LayerNorm (A/B runs)
     return !(e && e[0] == '0');
   }();
-  if (!enabled || N != kLnN || M <= kLnHalfM || K % kBK != 0) return false;
-  return (dtype == MMR_DT_BF16 ? ln_max_clusters<BF16>() : ln_max_clusters<FP16>()) > 0;
+  if (!enabled || N != kLnN || M <= kCtaRows || K % kBK != 0) return false;
+  return (dtype == MMR_DT_BF16 ? ln_max_pairs<BF16>() : ln_max_pairs<FP16>()) >= kLnTiles;
 }
 
 template <class E16>
-static mmr_status launch_ln(const CUtensorMap& ta, const CUtensorMap& tw, const GemmLnParams& p, cudaStream_t stream) {
-  const int tiles = (p.M + kLnBM - 1) / kLnBM;
-  const int max_clusters = ln_max_clusters<E16>();
-  const int grid = kLnCluster * (tiles < max_clusters ? tiles : max_clusters);
-  gemm_ln_kernel<E16><<<grid, kGemmThreads, kLnSmemBytes, stream>>>(ta, tw, p);
+static mmr_status launch_ln(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tr, const CUtensorMap& to32,
+                            const CUtensorMap& to16, const GemmLnParams& p, cudaStream_t stream) {
+  const int m_tiles = (p.M + kPairRows - 1) / kPairRows;
+  const int max_groups = ln_max_pairs<E16>() / kLnTiles;
+  const int groups = m_tiles < max_groups ? m_tiles : max_groups;
+  gemm_ln_kernel<E16><<<2 * kLnTiles * groups, kGemmThreads, kLnSmemBytes, stream>>>(ta, tw, tr, to32, to16, p);
   MMR_CUDA_OK(cudaGetLastError());
   return MMR_OK;
 }
@@ -370,16 +369,28 @@ mmr_status gemm_ln(const void* A16, int64_t lda, const void* W16, int64_t ldw, i
                    const float* residual, int64_t ldr, const float* gamma, const float* beta, float eps, void* out16,
                    int64_t ldo16, float* out32, int64_t ldo32, int dtype, cudaStream_t stream) {
   MMR_TRY(require_sm100());
-  MMR_REQUIRE(A16 && W16 && bias && residual && gamma && beta && (out16 || out32), "gemm_ln: null argument");
+  MMR_REQUIRE(A16 && W16 && bias && residual && gamma && beta && out16 && out32, "gemm_ln: null argument");
   MMR_REQUIRE(gemm_ln_eligible(M, kLnN, K, dtype), "gemm_ln: shape M=%d K=%d not eligible", M, K);
-  MMR_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && ldr % 4 == 0 && (!out32 || ldo32 % 4 == 0) && (!out16 || ldo16 % 4 == 0),
-              "gemm_ln: row strides break vector alignment");
-  CUtensorMap ta, tw;
-  MMR_TRY(make_tmap_2d(&ta, A16, M, K, lda, kLnHalfM, dtype));
-  MMR_TRY(make_tmap_2d(&tw, W16, kLnN, K, ldw, kLnHalfN, dtype));
-  GemmLnParams p{M, K, bias, residual, ldr, gamma, beta, eps, out16, ldo16, out32, ldo32, uint32_t(dtype)};
-  if (dtype == MMR_DT_BF16) return launch_ln<BF16>(ta, tw, p, stream);
-  return launch_ln<FP16>(ta, tw, p, stream);
+  MMR_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && ldr % 4 == 0 && ldo32 % 4 == 0 && ldo16 % 8 == 0,
+              "gemm_ln: row strides break 16-byte alignment");
+  MMR_REQUIRE(((reinterpret_cast<uintptr_t>(A16) | reinterpret_cast<uintptr_t>(W16) | reinterpret_cast<uintptr_t>(residual) |
+                reinterpret_cast<uintptr_t>(out16) | reinterpret_cast<uintptr_t>(out32) | reinterpret_cast<uintptr_t>(bias) |
+                reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0,
+              "gemm_ln: pointers must be 16-byte aligned");
+  MMR_TRY(gemm_ln_reserve(M));
+  int dev = 0;
+  MMR_CUDA_OK(cudaGetDevice(&dev));
+  const int ek = dtype == MMR_DT_BF16 ? 1 : 0;
+  CUtensorMap ta, tw, tr, to32, to16;
+  MMR_TRY(make_tmap_2d(&ta, A16, M, K, lda, kCtaRows, dtype));
+  MMR_TRY(make_tmap_2d(&tw, W16, kLnN, K, ldw, kBN / 2, dtype));
+  MMR_TRY(make_tmap_ex(&tr, residual, M, kLnN, ldr, 2, 32, 32, 128));
+  MMR_TRY(make_tmap_ex(&to32, out32, M, kLnN, ldo32, 2, 32, 32, 128));
+  MMR_TRY(make_tmap_ex(&to16, out16, M, kLnN, ldo16, ek, 32, 32, 64));
+  const LnWorkspace& ws = g_ln_ws[dev];
+  GemmLnParams p{M, K, bias, gamma, beta, eps, ws.stats, ws.counters, ws.counters + size_t(ws.m_tiles) * 8, uint32_t(dtype)};
+  if (dtype == MMR_DT_BF16) return launch_ln<BF16>(ta, tw, tr, to32, to16, p, stream);
+  return launch_ln<FP16>(ta, tw, tr, to32, to16, p, stream);
 }
 
 }  // namespace mmr

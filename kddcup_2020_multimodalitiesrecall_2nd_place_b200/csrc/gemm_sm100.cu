@@ -198,6 +198,30 @@ mmr_status make_tmap_2d(void* map_out, const void* base, int64_t rows, int64_t c
   return MMR_OK;
 }
 
+// General 2-D map: element kind 0 = fp16, 1 = bf16, 2 = fp32; box = box_cols x box_rows elements; swizzle_bytes is
+// 128, 64 or 0 and must equal the box's row size in bytes when non-zero (the epilogue staging layouts rely on it).
+mmr_status make_tmap_ex(void* map_out, const void* base, int64_t rows, int64_t cols, int64_t ld, int elem_kind,
+                        int box_cols, int box_rows, int swizzle_bytes) {
+  CUtensorMap* map = static_cast<CUtensorMap*>(map_out);
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return fail(MMR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const int esz = elem_kind == 2 ? 4 : 2;
+  const cuuint64_t gdim[2] = {cuuint64_t(cols), cuuint64_t(rows)};
+  const cuuint64_t gstride[1] = {cuuint64_t(ld) * esz};
+  const cuuint32_t box[2] = {cuuint32_t(box_cols), cuuint32_t(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapDataType dt = elem_kind == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : elem_kind == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                  : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                      : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MMR_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", int(r));
+  return MMR_OK;
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -260,6 +284,8 @@ mmr_status gemm(const void* A16, int64_t lda, const void* W16, int64_t ldw, int 
     const char* e = getenv("MMR_GEMM_PAIR");   // MMR_GEMM_PAIR=0 forces the single-CTA kernel (A/B measurements)
     return !(e && e[0] == '0');
   }();
+  if (pair_enabled && gemm_pair16_eligible(M, N, K, residual, out16, out32))
+    return gemm_pair16(A16, lda, W16, ldw, M, N, K, bias, out16, ldo16, act, dtype, stream);
   if (pair_enabled && gemm_pair_eligible(M, N, K)) {
     GemmParams pp{M, N, K, bias, residual, ldr, out16, ldo16, out32, ldo32, uint32_t(dtype), uint32_t(kBN / 2)};
     return gemm_pair(A16, lda, W16, ldw, pp, act, dtype, stream);

@@ -16,6 +16,7 @@ mmr_status attention(const void* q, int64_t ldq, const void* k, int64_t ldk, con
 mmr_status cast16(const float* x, void* out16, int64_t n, int dtype, cudaStream_t stream);
 // out = LN(A . W^T + bias + residual) for N = 768 in one kernel (gemm_ln_sm100.cu); residual may alias out32.
 bool gemm_ln_eligible(int M, int N, int K, int dtype);
+mmr_status gemm_ln_reserve(int M);   // exchange table for up to M rows on the current device (allocates; not in forward)
 mmr_status gemm_ln(const void* A16, int64_t lda, const void* W16, int64_t ldw, int M, int K, const float* bias,
                    const float* residual, int64_t ldr, const float* gamma, const float* beta, float eps, void* out16,
                    int64_t ldo16, float* out32, int64_t ldo32, int dtype, cudaStream_t stream);

@@ -743,6 +743,8 @@ extern "C" mmr_status mmr_create(const mmr_config* cfg, const mmr_tensor* weight
     }
   }
   if (rc == MMR_OK) rc = alloc_workspace(h);
+  if (rc == MMR_OK && gemm_ln_eligible(int(h->rows_max), cfg->hidden, cfg->hidden, cfg->dtype))
+    rc = gemm_ln_reserve(int(h->rows_max));
   if (rc != MMR_OK) {
     mmr_destroy(h);
     return rc;

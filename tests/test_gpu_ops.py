@@ -63,6 +63,32 @@ def test_gemm_residual_in_place_and_baseline_shapes():
     assert _rel(x, ref) < 2e-5
 
 
+@pytest.mark.parametrize("M,N,K,act", [(300, 256, 128, 0), (1000, 768, 768, 2), (17408, 2304, 768, 0),
+                                       (17408, 3072, 768, 2), (9216, 768, 2048, 1), (8192, 3072, 768, 3),
+                                       (19200, 512, 64, 0), (129, 1024, 192, 4)])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_gemm_16bit_output_path(M, N, K, act, dtype):
+    """out16-only GEMM (QKV / FFN-in class): CTA-pair kernel with the TMA-store epilogue, including the split tail
+    wave (N = 2304 -> 2 x 128-wide sub-tiles, N = 3072 -> 4 x 64-wide), ragged M and a strided output view."""
+    from kddcup_2020_multimodalitiesrecall_2nd_place_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda").to(dtype)
+    w = (torch.randn(N, K, device="cuda") * 0.05).to(dtype)
+    b = torch.randn(N, device="cuda") * 0.1
+    ldo = N + 64                                        # output is a column slice of a wider buffer
+    out = torch.full((M + 3, ldo), 7.0, device="cuda", dtype=dtype)
+    _lib.check(lib.mmr_gemm(a.data_ptr(), K, w.data_ptr(), K, M, N, K, b.data_ptr(), 0, 0, out.data_ptr(), ldo, 0, 0,
+                            act, _lib.DT_FP16 if dtype == torch.float16 else _lib.DT_BF16,
+                            torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t() + b
+    ref = {0: lambda x: x, 1: F.relu, 2: lambda x: F.gelu(x, approximate="tanh"), 3: F.gelu, 4: torch.tanh}[act](ref)
+    assert _rel(out[:M, :N], ref) < (4e-3 if dtype == torch.bfloat16 else 6e-4)
+    # nothing outside [M, N] was touched (TMA stores clip at the tensor-map bounds)
+    assert (out[M:] == 7.0).all() and (out[:, N:] == 7.0).all()
+
+
 def test_gemm_rejects_bad_arguments():
     from kddcup_2020_multimodalitiesrecall_2nd_place_b200 import ops
     from kddcup_2020_multimodalitiesrecall_2nd_place_b200._lib import MmrError
