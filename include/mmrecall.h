@@ -92,6 +92,18 @@ mmr_status mmr_gemm_layernorm(const void* A16, int64_t lda, const void* W16, int
                               int dtype, void* stream);
 int mmr_gemm_layernorm_supported(int M, int K, int dtype);
 
+/* Match heads on pooled [B, width] fp32 rows (device pointers), the last step of every scorer.
+ * mmr_am_softmax_head: model_triple.amsoftmax_loss, imagebert_zk/model_triple.py:56-86 (inference): x/|x|, cosine with
+ *   the COLUMN-NORMALISED kernel wn [2, 768] (l2_normalize(kernel, 0, 1e-10) done by the caller once), clip, margin
+ *   0.35 on the fed label's cosine when it exceeds 0.35, x30, softmax.  logits may be NULL.
+ * mmr_linear_head: optional LayerNorm(width, eps 1e-12) then W [2, width] + bias, softmax:
+ *   get_next_sentence_output, imagebert_lds/src/run_pretraining_predict_score.py:479-501 (ln_gamma = NULL, width 768)
+ *   and the tail of logit_fc, lxmert/src/tasks/kdd_model.py:167-172 (width 1536). */
+mmr_status mmr_am_softmax_head(const float* pooled, const float* wn, const int32_t* labels, int B, float* probs,
+                               float* logits, void* stream);
+mmr_status mmr_linear_head(const float* x, int width, const float* ln_gamma, const float* ln_beta, const float* W,
+                           const float* bias, int B, float* probs, float* logits, void* stream);
+
 /* Multi-head scaled-dot-product attention, softmax in fp32, additive key mask (1-m)*-10000:
  * pixelbert.py:790-850 / modeling.py:325-352.  q [B*Sq, ldq], k/v [B*Sk, ldk/ldv], head h = columns
  * [64h, 64h+64).  key_mask dev int32 [B,Sk] (1 = attend) or NULL.  Sq, Sk <= 128. */

@@ -468,3 +468,18 @@ mmr_status linear_head(const float* x, int width, const float* ln_gamma, const f
 }
 
 }  // namespace mmr
+
+extern "C" mmr_status mmr_am_softmax_head(const float* pooled, const float* wn, const int32_t* labels, int B,
+                                          float* probs, float* logits, void* stream) {
+  MMR_TRY(mmr::require_sm100());
+  MMR_REQUIRE(pooled && wn && labels && probs && B > 0, "mmr_am_softmax_head: null argument");
+  return mmr::zk_head(pooled, wn, labels, B, probs, logits, static_cast<cudaStream_t>(stream));
+}
+extern "C" mmr_status mmr_linear_head(const float* x, int width, const float* ln_gamma, const float* ln_beta,
+                                      const float* W, const float* bias, int B, float* probs, float* logits,
+                                      void* stream) {
+  MMR_TRY(mmr::require_sm100());
+  MMR_REQUIRE(x && W && bias && probs && B > 0, "mmr_linear_head: null argument");
+  MMR_REQUIRE((ln_gamma == nullptr) == (ln_beta == nullptr), "mmr_linear_head: give both LayerNorm vectors or none");
+  return mmr::linear_head(x, width, ln_gamma, ln_beta, W, bias, B, probs, logits, static_cast<cudaStream_t>(stream));
+}
