@@ -54,6 +54,18 @@ typedef enum {
 
 const char* mmr_last_error(void);
 int mmr_abi_version(void);
+/* Kernel-selection knobs, for A/B measurements and tests (defaults are the fastest measured; the environment
+ * variable of the same meaning is read once at first use): value 0 disables / selects the older path.
+ *   MMR_TUNE_GEMM_PAIR     (env MMR_GEMM_PAIR,    default 1) CTA-pair (cta_group::2) GEMM kernels
+ *   MMR_TUNE_GEMM_P16      (env MMR_GEMM_P16,     default 1) 16-bit-output GEMM with the TMA-store epilogue
+ *   MMR_TUNE_GEMM_TAIL     (env MMR_GEMM_TAIL,    default 1) split the last partial wave of that GEMM along N
+ *   MMR_TUNE_GEMM_CLUSTER  (env MMR_GEMM_CLUSTER, default 1) 1 = lone CTA pairs, 2 = 4-CTA clusters sharing W by
+ *                                                            TMA multicast (measured slower: 132 of 148 SMs)
+ *   MMR_TUNE_GEMM_LN       (env MMR_GEMM_LN,      default 1) fused projection + residual + LayerNorm kernel
+ *   MMR_TUNE_PDL           (env MMR_PDL,          default 1) programmatic dependent launch between the kernels */
+enum { MMR_TUNE_GEMM_PAIR = 0, MMR_TUNE_GEMM_P16 = 1, MMR_TUNE_GEMM_TAIL = 2, MMR_TUNE_GEMM_CLUSTER = 3,
+       MMR_TUNE_GEMM_LN = 4, MMR_TUNE_PDL = 5, MMR_TUNE_COUNT = 6 };
+mmr_status mmr_set_tuning(int knob, int value);
 /* MMR_OK iff `device` is an sm_100 part. */
 mmr_status mmr_device_check(int device);
 

@@ -59,6 +59,8 @@ attention_kernel(const typename E16::T* __restrict__ q, int64_t ldq, const typen
                  int Sk) {
   using T = typename E16::T;
   extern __shared__ __align__(16) uint8_t smem_att[];
+  pdl_wait();
+  pdl_launch_dependents();
   const int h = blockIdx.x, b = blockIdx.y;
   const int nwarps = blockDim.x >> 5;
   const int SqP = nwarps * 16;
@@ -219,10 +221,9 @@ static mmr_status launch_attention(const void* q, int64_t ldq, const void* k, in
   }
   const int nwarps = (Sq + 15) / 16;
   dim3 grid(heads, B);
-  kern<<<grid, nwarps * 32, attention_smem_bytes(Sq, Sk), stream>>>(
-      static_cast<const T*>(q), ldq, static_cast<const T*>(k), ldk, static_cast<const T*>(v), ldv, key_mask,
-      static_cast<T*>(out), ldo, Sq, Sk);
-  MMR_CUDA_OK(cudaGetLastError());
+  MMR_CUDA_OK(launch_pdl(kern, grid, dim3(nwarps * 32), attention_smem_bytes(Sq, Sk), stream, static_cast<const T*>(q),
+                         ldq, static_cast<const T*>(k), ldk, static_cast<const T*>(v), ldv, key_mask,
+                         static_cast<T*>(out), ldo, Sq, Sk));
   return MMR_OK;
 }
 

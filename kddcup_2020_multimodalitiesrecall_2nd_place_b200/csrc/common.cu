@@ -1,4 +1,6 @@
 // Error state and device gate behind the C ABI.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace mmr {
@@ -14,6 +16,23 @@ mmr_status fail(mmr_status code, const char* fmt, ...) {
   vsnprintf(last_error_buf(), 512, fmt, ap);
   va_end(ap);
   return code;
+}
+
+// knob -> {environment variable, default}
+static int g_tuning[MMR_TUNE_COUNT];
+static bool g_tuning_init = false;
+static void tuning_init() {
+  static const struct { const char* env; int def; } spec[MMR_TUNE_COUNT] = {
+      {"MMR_GEMM_PAIR", 1}, {"MMR_GEMM_P16", 1}, {"MMR_GEMM_TAIL", 1}, {"MMR_GEMM_CLUSTER", 1}, {"MMR_GEMM_LN", 1}, {"MMR_PDL", 1}};
+  for (int i = 0; i < MMR_TUNE_COUNT; ++i) {
+    const char* e = getenv(spec[i].env);
+    g_tuning[i] = e ? atoi(e) : spec[i].def;
+  }
+  g_tuning_init = true;
+}
+int tuning(int knob) {
+  if (!g_tuning_init) tuning_init();
+  return (knob >= 0 && knob < MMR_TUNE_COUNT) ? g_tuning[knob] : 0;
 }
 
 mmr_status require_sm100() {
@@ -45,6 +64,12 @@ mmr_status require_sm100() {
 
 extern "C" const char* mmr_last_error(void) { return mmr::last_error_buf(); }
 extern "C" int mmr_abi_version(void) { return 1; }
+extern "C" mmr_status mmr_set_tuning(int knob, int value) {
+  if (knob < 0 || knob >= MMR_TUNE_COUNT) return mmr::fail(MMR_ERR_INVALID, "mmr_set_tuning: unknown knob %d", knob);
+  if (!mmr::g_tuning_init) mmr::tuning_init();
+  mmr::g_tuning[knob] = value;
+  return MMR_OK;
+}
 extern "C" mmr_status mmr_device_check(int device) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) {

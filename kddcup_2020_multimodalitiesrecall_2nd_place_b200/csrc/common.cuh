@@ -34,8 +34,28 @@ mmr_status fail(mmr_status code, const char* fmt, ...);
     if (!(cond)) return ::mmr::fail(MMR_ERR_INVALID, __VA_ARGS__); \
   } while (0)
 
+// Tuning knobs (mmr_set_tuning / environment at first use); see include/mmrecall.h for the indices.
+int tuning(int knob);
+
 // MMR_OK iff the *current* device is sm_100; cached per device.
 mmr_status require_sm100();
+
+// ---- kernel launch with programmatic dependent launch (see ptx.cuh: pdl_wait / pdl_launch_dependents) ----
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = tuning(MMR_TUNE_PDL) != 0 ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 // ---- 16-bit element traits ----
 struct BF16 {

@@ -11,6 +11,7 @@
 //   heads: AM-softmax (model_triple.py:56-86), linear 2-way (run_pretraining_predict_score.py:479-501),
 //       LayerNorm(1536) + linear 2-way (tasks/kdd_model.py:167-172), each followed by softmax.
 #include "common.cuh"
+#include "ptx.cuh"
 #include "kernels.cuh"
 
 namespace mmr {
@@ -95,6 +96,8 @@ zk_region_sum_kernel(const float* __restrict__ feat32, const float* __restrict__
                      const int32_t* __restrict__ label_ids, const float* __restrict__ tables, int vocab,
                      const float* __restrict__ bc1, const float* __restrict__ Wb, const float* __restrict__ bb,
                      typename E16::T* __restrict__ out16, int rows) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -141,6 +144,8 @@ zk_embed_kernel(const int32_t* __restrict__ query_ids, const int32_t* __restrict
                 const float* __restrict__ P, const float* __restrict__ gamma, const float* __restrict__ beta,
                 int Lq, int R, int rows, typename E16::T* __restrict__ x16, float* __restrict__ x32,
                 int32_t* __restrict__ key_mask) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -168,6 +173,8 @@ lds_embed_kernel(const int32_t* __restrict__ query_ids, const int32_t* __restric
                  const float* __restrict__ E, const float* __restrict__ T, const float* __restrict__ P,
                  const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ wl,
                  int Lq, int R, int rows, typename E16::T* __restrict__ x16, float* __restrict__ x32) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -215,6 +222,8 @@ lx_lang_embed_kernel(const int32_t* __restrict__ query_ids, const float* __restr
                      const float* __restrict__ T, const float* __restrict__ P, const float* __restrict__ gamma,
                      const float* __restrict__ beta, int Lq, int rows, typename E16::T* __restrict__ x16,
                      float* __restrict__ x32) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -234,6 +243,8 @@ lx_label_z_kernel(const int32_t* __restrict__ label_ids, const float* __restrict
                   const float* __restrict__ P, const float* __restrict__ gamma, const float* __restrict__ beta,
                   const float* __restrict__ wconv, const float* __restrict__ bconv, int rows,
                   typename E16::T* __restrict__ z16) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -257,6 +268,8 @@ __global__ void __launch_bounds__(256)
 lx_box_ln_kernel(const float* __restrict__ boxes4, const float* __restrict__ Wb, const float* __restrict__ bb,
                  const float* __restrict__ gamma, const float* __restrict__ beta, float scale, int rows,
                  float* __restrict__ acc32) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -298,6 +311,8 @@ __device__ __forceinline__ void softmax2(float l0, float l1, float* out) {
 __global__ void __launch_bounds__(256)
 zk_head_kernel(const float* __restrict__ pooled, const float* __restrict__ wn, const int32_t* __restrict__ labels,
                int B, float* __restrict__ probs, float* __restrict__ logits) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
   const int lane = threadIdx.x & 31;
@@ -331,6 +346,8 @@ __global__ void __launch_bounds__(256)
 linear_head_kernel(const float* __restrict__ x, int width, const float* __restrict__ ln_gamma,
                    const float* __restrict__ ln_beta, const float* __restrict__ W, const float* __restrict__ bias,
                    int B, float* __restrict__ probs, float* __restrict__ logits) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
   const int lane = threadIdx.x & 31;
@@ -394,7 +411,7 @@ static inline int blocks_for(int rows) { return (rows + 7) / 8; }
 mmr_status zk_region_sum(const float* feat32, const float* boxes5, const int32_t* label_ids, const float* tables,
                          int vocab, const float* bc1, const float* Wb, const float* bb, void* out16, int rows,
                          int dtype, cudaStream_t st) {
-  MMR_DISPATCH16(dtype, (zk_region_sum_kernel<E16><<<blocks_for(rows), 256, 0, st>>>(
+  MMR_DISPATCH16(dtype, ((void)launch_pdl(zk_region_sum_kernel<E16>, dim3(blocks_for(rows)), dim3(256), 0, st, 
                             feat32, boxes5, label_ids, tables, vocab, bc1, Wb, bb,
                             static_cast<typename E16::T*>(out16), rows)));
   MMR_CUDA_OK(cudaGetLastError());
@@ -406,7 +423,7 @@ mmr_status zk_embed(const int32_t* query_ids, const int32_t* segment_ids, const 
                     const float* P, const float* gamma, const float* beta, int Lq, int R, int B, void* x16,
                     float* x32, int32_t* key_mask, int dtype, cudaStream_t st) {
   const int rows = B * (Lq + R);
-  MMR_DISPATCH16(dtype, (zk_embed_kernel<E16><<<blocks_for(rows), 256, 0, st>>>(
+  MMR_DISPATCH16(dtype, ((void)launch_pdl(zk_embed_kernel<E16>, dim3(blocks_for(rows)), dim3(256), 0, st, 
                             query_ids, segment_ids, region32, len_query, num_boxes, E, T, P, gamma, beta, Lq, R,
                             rows, static_cast<typename E16::T*>(x16), x32, key_mask)));
   MMR_CUDA_OK(cudaGetLastError());
@@ -418,7 +435,7 @@ mmr_status lds_embed(const int32_t* query_ids, const int32_t* segment_ids, const
                      const float* beta, const float* wl, int Lq, int R, int B, void* x16, float* x32, int dtype,
                      cudaStream_t st) {
   const int rows = B * (Lq + 2 * R);
-  MMR_DISPATCH16(dtype, (lds_embed_kernel<E16><<<blocks_for(rows), 256, 0, st>>>(
+  MMR_DISPATCH16(dtype, ((void)launch_pdl(lds_embed_kernel<E16>, dim3(blocks_for(rows)), dim3(256), 0, st, 
                             query_ids, segment_ids, label_ids, region32, E, T, P, gamma, beta, wl, Lq, R, rows,
                             static_cast<typename E16::T*>(x16), x32)));
   MMR_CUDA_OK(cudaGetLastError());
@@ -429,7 +446,7 @@ mmr_status lx_lang_embed(const int32_t* query_ids, const float* E, const float* 
                          const float* gamma, const float* beta, int Lq, int B, void* x16, float* x32, int dtype,
                          cudaStream_t st) {
   const int rows = B * Lq;
-  MMR_DISPATCH16(dtype, (lx_lang_embed_kernel<E16><<<blocks_for(rows), 256, 0, st>>>(
+  MMR_DISPATCH16(dtype, ((void)launch_pdl(lx_lang_embed_kernel<E16>, dim3(blocks_for(rows)), dim3(256), 0, st, 
                             query_ids, E, T, P, gamma, beta, Lq, rows, static_cast<typename E16::T*>(x16), x32)));
   MMR_CUDA_OK(cudaGetLastError());
   return MMR_OK;
@@ -438,7 +455,7 @@ mmr_status lx_lang_embed(const int32_t* query_ids, const float* E, const float* 
 mmr_status lx_label_z(const int32_t* label_ids, const float* E, const float* T, const float* P,
                       const float* gamma, const float* beta, const float* wconv, const float* bconv, int rows,
                       void* z16, int dtype, cudaStream_t st) {
-  MMR_DISPATCH16(dtype, (lx_label_z_kernel<E16><<<blocks_for(rows), 256, 0, st>>>(
+  MMR_DISPATCH16(dtype, ((void)launch_pdl(lx_label_z_kernel<E16>, dim3(blocks_for(rows)), dim3(256), 0, st, 
                             label_ids, E, T, P, gamma, beta, wconv, bconv, rows,
                             static_cast<typename E16::T*>(z16))));
   MMR_CUDA_OK(cudaGetLastError());
@@ -447,14 +464,14 @@ mmr_status lx_label_z(const int32_t* label_ids, const float* E, const float* T, 
 
 mmr_status lx_box_ln(const float* boxes4, const float* Wb, const float* bb, const float* gamma, const float* beta,
                      float scale, int rows, float* acc32, cudaStream_t st) {
-  lx_box_ln_kernel<<<blocks_for(rows), 256, 0, st>>>(boxes4, Wb, bb, gamma, beta, scale, rows, acc32);
+  (void)launch_pdl(lx_box_ln_kernel, dim3(blocks_for(rows)), dim3(256), 0, st, boxes4, Wb, bb, gamma, beta, scale, rows, acc32);
   MMR_CUDA_OK(cudaGetLastError());
   return MMR_OK;
 }
 
 mmr_status zk_head(const float* pooled, const float* wn, const int32_t* labels, int B, float* probs, float* logits,
                    cudaStream_t st) {
-  zk_head_kernel<<<blocks_for(B), 256, 0, st>>>(pooled, wn, labels, B, probs, logits);
+  (void)launch_pdl(zk_head_kernel, dim3(blocks_for(B)), dim3(256), 0, st, pooled, wn, labels, B, probs, logits);
   MMR_CUDA_OK(cudaGetLastError());
   return MMR_OK;
 }
@@ -462,7 +479,7 @@ mmr_status zk_head(const float* pooled, const float* wn, const int32_t* labels, 
 mmr_status linear_head(const float* x, int width, const float* ln_gamma, const float* ln_beta, const float* W,
                        const float* bias, int B, float* probs, float* logits, cudaStream_t st) {
   MMR_REQUIRE(width % 128 == 0 && width <= 1536, "linear_head: width %d unsupported", width);
-  linear_head_kernel<<<blocks_for(B), 256, 0, st>>>(x, width, ln_gamma, ln_beta, W, bias, B, probs, logits);
+  (void)launch_pdl(linear_head_kernel, dim3(blocks_for(B)), dim3(256), 0, st, x, width, ln_gamma, ln_beta, W, bias, B, probs, logits);
   MMR_CUDA_OK(cudaGetLastError());
   return MMR_OK;
 }

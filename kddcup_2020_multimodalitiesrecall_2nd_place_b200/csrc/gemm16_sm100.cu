@@ -25,6 +25,9 @@
 
 namespace mmr {
 
+// Warp roles: the SM's warp arbiter favours HIGHER warp ids, so the two single-thread roles whose latency the whole
+// pipeline hangs on (TMA producer, MMA issuer) take the highest ids and the eight epilogue warps ids 0..7.
+constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
 constexpr int kP16WarpStage = 2 * 2048;             // two [32 rows x 64 B] store stages per epilogue warp
 template <int STAGES>
 constexpr size_t p16_smem_bytes() {
@@ -35,14 +38,23 @@ struct P16Params {
   int M, N, K;
   const float* bias;     // [N] or null
   uint32_t idesc_fmt;    // 0 fp16 / 1 bf16
-  int full_tiles;        // tiles [0, full_tiles) are 256 x 256; the rest are the split tail
-  int tail_split_log2;   // 0, 1 or 2: tail tiles are 256 x (256 >> s)
+  int full_tiles;        // work items [0, full_tiles) are 256 columns wide; the rest are the split tail
+  int tail_split_log2;   // 0, 1 or 2: tail items are (256 >> s) columns wide
+  int total_items;       // full_tiles + (remaining items << s)
+  unsigned long long* trace;   // debug: [cluster][32][4] ns stamps (entry, prologue done, per tile MMA / epilogue), or null
 };
+__device__ __forceinline__ unsigned long long p16_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// A work item is one column tile of one row GROUP: a group is 256 rows for a lone pair (CP = 1) and 512 rows for a
+// 4-CTA cluster (CP = 2), whose two pairs take its upper and lower 256-row block.
 
 struct TileCoord {
   int m_blk, col0, bn;
 };
-// Tile index -> (row block, first column, width).  n_tiles = N / 256.
+// Work item -> (row group, first column, width).  n_tiles = N / 256.
 __device__ __forceinline__ TileCoord p16_tile(const P16Params& p, int tile, int n_tiles) {
   TileCoord t;
   if (tile < p.full_tiles) {
@@ -60,8 +72,8 @@ __device__ __forceinline__ TileCoord p16_tile(const P16Params& p, int tile, int 
   return t;
 }
 
-template <int ACT, class E16, int STAGES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+template <int ACT, class E16, int STAGES, int CP>
+__global__ void __cluster_dims__(2 * CP, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_pair16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                    const __grid_constant__ CUtensorMap tmap_w_tail, const __grid_constant__ CUtensorMap tmap_o,
                    const P16Params p) {
@@ -75,23 +87,26 @@ gemm_pair16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();        // 0 = leader
-  const int pair = blockIdx.x >> 1;
-  const int n_pairs = gridDim.x >> 1;
+  const unsigned long long t_entry = p16_now();
+  const uint32_t crank = cluster_ctarank();
+  const uint32_t rank = crank & 1u;               // row half within the pair; 0 = the pair's MMA-issuing CTA
+  const uint32_t cpair = crank >> 1;              // which pair of the cluster (always 0 when CP = 1)
+  const uint32_t leader = crank & ~1u;            // cluster rank of this pair's leader
+  const int pair = blockIdx.x / (2 * CP);         // work-item stride unit: the cluster
+  const int n_pairs = gridDim.x / (2 * CP);
   const int n_tiles = p.N / kBN;
   const int k_blocks = p.K / kBK;
-  const int m_tiles = (p.M + kPairRows - 1) / kPairRows;
-  const int total_tiles = p.full_tiles + ((m_tiles * n_tiles - p.full_tiles) << p.tail_split_log2);
+  const int total_tiles = p.total_items;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kProducerWarp && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_w);
     tma_prefetch_desc(&tmap_w_tail);
     tma_prefetch_desc(&tmap_o);
-    ring.init(2 * kEpiWarps);
+    ring.init(2 * kEpiWarps, CP);
     fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tmem_alloc_2sm(tmem_slot, kTmemCols);
     tmem_relinquish_2sm();
   }
@@ -100,40 +115,48 @@ gemm_pair16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   cluster_sync_all();   // the peer's barriers are initialised before any remote arrive / TMA credit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                 // the previous kernel's outputs (this one's operands / residual) are complete
+  pdl_launch_dependents();    // the next kernel may be scheduled as soon as SMs free up
 
-  if (warp == 0) {
+  if (warp == kProducerWarp) {
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
       RingPos pos;
       for (int tile = pair; tile < total_tiles; tile += n_pairs) {
         const TileCoord t = p16_tile(p, tile, n_tiles);
         const int w_rows = t.bn / 2;
-        pair_produce_tile<STAGES>(ring, pos, &tmap_a, t.bn == kBN ? &tmap_w : &tmap_w_tail,
-                                      t.m_blk * kPairRows + int(rank) * kCtaRows, t.col0 + int(rank) * w_rows, w_rows,
-                                      k_blocks, rank, 0);
+        pair_produce_tile<STAGES, CP>(ring, pos, &tmap_a, t.bn == kBN ? &tmap_w : &tmap_w_tail,
+                                      (t.m_blk * CP + int(cpair)) * kPairRows + int(rank) * kCtaRows,
+                                      t.col0 + int(rank) * w_rows, w_rows, k_blocks, rank, leader, cpair);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (leader CTA, one thread) =====================
     if (rank == 0 && lane == 0) {
       RingPos pos;
       int it = 0;
+      if (p.trace != nullptr && cpair == 0) {
+        p.trace[size_t(pair) * 128 + 0] = t_entry;
+        p.trace[size_t(pair) * 128 + 1] = p16_now();
+      }
       for (int tile = pair; tile < total_tiles; tile += n_pairs, ++it) {
         const TileCoord t = p16_tile(p, tile, n_tiles);
         const int acc = it & 1;
+        if (p.trace != nullptr && cpair == 0 && it < 30) p.trace[size_t(pair) * 128 + 4 + 4 * it] = p16_now();
         pair_mma_tile<STAGES>(ring, pos, tmem_base + uint32_t(acc) * kBN,
                                   umma_idesc_f16(p.idesc_fmt, kPairRows, uint32_t(t.bn)), k_blocks, acc,
-                                  (it >> 1) & 1u, 0b11);
+                                  (it >> 1) & 1u, uint16_t(0b11u << leader), uint16_t((1u << (2 * CP)) - 1u));
+        if (p.trace != nullptr && cpair == 0 && it < 30) p.trace[size_t(pair) * 128 + 4 + 4 * it + 1] = p16_now();
       }
     }
   } else {
     // ===================== epilogue warps (both CTAs, own 128 rows) =====================
-    const int ew = warp - 2;
+    const int ew = warp;                   // epilogue warps are warps 0..7
     const int quarter = warp & 3;          // TMEM lane quarter this warp may touch
     const int half = ew >> 2;              // which half of the tile's columns
     uint8_t* stage0 = out_stage + size_t(ew) * kP16WarpStage;
-    const uint32_t tempty_leader0 = mapa_u32(smem_u32(&ring.tempty[0]), 0);
-    const uint32_t tempty_leader1 = mapa_u32(smem_u32(&ring.tempty[1]), 0);
+    const uint32_t tempty_leader0 = mapa_u32(smem_u32(&ring.tempty[0]), leader);
+    const uint32_t tempty_leader1 = mapa_u32(smem_u32(&ring.tempty[1]), leader);
     const uint32_t sw64 = uint32_t((lane >> 1) & 3);
     uint32_t n_store = 0;
     int it = 0;
@@ -143,10 +166,11 @@ gemm_pair16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const int wcols = t.bn / 2;                       // columns owned by this warp: 128, 64 or 32
       const int wcol0 = t.col0 + half * wcols;
       const int n_chunks = wcols / 32;                  // 4, 2 or 1
-      const int row0 = t.m_blk * kPairRows + int(rank) * kCtaRows + quarter * 32;
+      const int row0 = (t.m_blk * CP + int(cpair)) * kPairRows + int(rank) * kCtaRows + quarter * 32;
       const uint32_t taddr = tmem_base + uint32_t(acc) * kBN + (uint32_t(quarter * 32) << 16) + uint32_t(half * wcols);
       mbar_wait(&ring.tfull[acc], (it >> 1) & 1u);
       tc_fence_after();
+      if (p.trace != nullptr && crank == 0 && ew == 0 && lane == 0 && it < 30) p.trace[size_t(pair) * 128 + 4 + 4 * it + 2] = p16_now();
 #pragma unroll 1
       for (int c = 0; c < n_chunks; ++c) {
         uint8_t* buf = stage0 + ((n_store & 1u) ? 2048 : 0);
@@ -191,6 +215,7 @@ gemm_pair16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         }
         ++n_store;
       }
+      if (p.trace != nullptr && crank == 0 && ew == 0 && lane == 0 && it < 30) p.trace[size_t(pair) * 128 + 4 + 4 * it + 3] = p16_now();
     }
     if (lane == 0) bulk_wait<0>();   // stores complete (and their smem reads with them) before the CTA retires
   }
@@ -198,92 +223,117 @@ gemm_pair16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();   // no CTA leaves while its peer may still read its smem or signal its barriers
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc_2sm(tmem_base, kTmemCols);
   }
+  if (p.trace != nullptr && crank == 0 && threadIdx.x == 0) p.trace[size_t(pair) * 128 + 2] = p16_now();
 }
 
-template <int ACT, class E16, int STAGES>
+template <int ACT, class E16, int STAGES, int CP>
 static mmr_status launch_p16s(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& twt,
                               const CUtensorMap& to, const P16Params& p, int grid, cudaStream_t stream) {
-  auto kern = gemm_pair16_kernel<ACT, E16, STAGES>;
+  auto kern = gemm_pair16_kernel<ACT, E16, STAGES, CP>;
   static bool configured = false;
   if (!configured) {
     MMR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(p16_smem_bytes<STAGES>())));
     configured = true;
   }
-  kern<<<grid, kGemmThreads, p16_smem_bytes<STAGES>(), stream>>>(ta, tw, twt, to, p);
-  MMR_CUDA_OK(cudaGetLastError());
+  MMR_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(kGemmThreads), p16_smem_bytes<STAGES>(), stream, ta, tw, twt, to, p));
   return MMR_OK;
 }
+constexpr int kP16Stages = 6;
 template <int ACT, class E16>
 static mmr_status launch_p16(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& twt, const CUtensorMap& to,
-                             const P16Params& p, int grid, cudaStream_t stream) {
-  static const int stages = [] {
-    const char* e = getenv("MMR_P16_STAGES");   // pipeline-depth experiment (profiles/r01e_*)
-    return e ? atoi(e) : 6;
-  }();
-  switch (stages) {
-    case 3: return launch_p16s<ACT, E16, 3>(ta, tw, twt, to, p, grid, stream);
-    case 4: return launch_p16s<ACT, E16, 4>(ta, tw, twt, to, p, grid, stream);
-    case 5: return launch_p16s<ACT, E16, 5>(ta, tw, twt, to, p, grid, stream);
-    default: return launch_p16s<ACT, E16, 6>(ta, tw, twt, to, p, grid, stream);
+                             const P16Params& p, int grid, int cluster_pairs, cudaStream_t stream) {
+  if (cluster_pairs == 2) return launch_p16s<ACT, E16, kP16Stages, 2>(ta, tw, twt, to, p, grid, stream);
+  return launch_p16s<ACT, E16, kP16Stages, 1>(ta, tw, twt, to, p, grid, stream);
+}
+
+// Co-resident 4-CTA clusters of this kernel on the current device (0: none).  All instantiations share the launch
+// shape, so one query serves them all.
+static int p16_max_quads() {
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  auto kern = gemm_pair16_kernel<MMR_ACT_NONE, FP16, kP16Stages, 2>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(p16_smem_bytes<kP16Stages>())) !=
+      cudaSuccess) {
+    cudaGetLastError();
+    return cached = 0;
   }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(4 * 37, 1, 1);
+  cfg.blockDim = dim3(kGemmThreads, 1, 1);
+  cfg.dynamicSmemBytes = p16_smem_bytes<kP16Stages>();
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 4;
+  attr.val.clusterDim.y = 1;
+  attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  return cached = n;
 }
 
 template <class E16>
 static mmr_status dispatch_p16(int act, const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& twt,
-                               const CUtensorMap& to, const P16Params& p, int grid, cudaStream_t s) {
+                               const CUtensorMap& to, const P16Params& p, int grid, int cp, cudaStream_t s) {
   switch (act) {
-    case MMR_ACT_NONE: return launch_p16<MMR_ACT_NONE, E16>(ta, tw, twt, to, p, grid, s);
-    case MMR_ACT_RELU: return launch_p16<MMR_ACT_RELU, E16>(ta, tw, twt, to, p, grid, s);
-    case MMR_ACT_GELU_TANH: return launch_p16<MMR_ACT_GELU_TANH, E16>(ta, tw, twt, to, p, grid, s);
-    case MMR_ACT_GELU_ERF: return launch_p16<MMR_ACT_GELU_ERF, E16>(ta, tw, twt, to, p, grid, s);
-    case MMR_ACT_TANH: return launch_p16<MMR_ACT_TANH, E16>(ta, tw, twt, to, p, grid, s);
+    case MMR_ACT_NONE: return launch_p16<MMR_ACT_NONE, E16>(ta, tw, twt, to, p, grid, cp, s);
+    case MMR_ACT_RELU: return launch_p16<MMR_ACT_RELU, E16>(ta, tw, twt, to, p, grid, cp, s);
+    case MMR_ACT_GELU_TANH: return launch_p16<MMR_ACT_GELU_TANH, E16>(ta, tw, twt, to, p, grid, cp, s);
+    case MMR_ACT_GELU_ERF: return launch_p16<MMR_ACT_GELU_ERF, E16>(ta, tw, twt, to, p, grid, cp, s);
+    case MMR_ACT_TANH: return launch_p16<MMR_ACT_TANH, E16>(ta, tw, twt, to, p, grid, cp, s);
     default: return fail(MMR_ERR_INVALID, "mmr_gemm: unknown activation %d", act);
   }
 }
 
+static unsigned long long* g_p16_trace = nullptr;
 bool gemm_pair16_eligible(int M, int N, int K, const float* residual, const void* out16, const float* out32) {
-  static const bool enabled = [] {
-    const char* e = getenv("MMR_GEMM_P16");   // MMR_GEMM_P16=0: use the general pair kernel (A/B measurements)
-    return !(e && e[0] == '0');
-  }();
-  return enabled && N % kBN == 0 && M > kCtaRows && K % kBK == 0 && residual == nullptr && out32 == nullptr &&
+  return tuning(MMR_TUNE_GEMM_P16) != 0 && N % kBN == 0 && M > kCtaRows && K % kBK == 0 && residual == nullptr && out32 == nullptr &&
          out16 != nullptr;
 }
 
 // Arguments are already validated by mmr::gemm.
 mmr_status gemm_pair16(const void* A16, int64_t lda, const void* W16, int64_t ldw, int M, int N, int K,
                        const float* bias, void* out16, int64_t ldo16, int act, int dtype, cudaStream_t stream) {
-  static const bool split_tail = [] {
-    const char* e = getenv("MMR_GEMM_TAIL");   // MMR_GEMM_TAIL=0 disables the split tail wave
-    return !(e && e[0] == '0');
-  }();
+  const bool split_tail = tuning(MMR_TUNE_GEMM_TAIL) != 0;
+  const int want_cp = tuning(MMR_TUNE_GEMM_CLUSTER);
   const int m_tiles = (M + kPairRows - 1) / kPairRows, n_tiles = N / kBN;
-  const int tiles = m_tiles * n_tiles;
-  const int max_pairs = sm_count() / 2;
-  P16Params p{M, N, K, bias, uint32_t(dtype), tiles, 0};
-  const int rem = tiles % max_pairs;
-  if (split_tail && tiles > max_pairs && rem != 0) {
-    // split the last partial wave so that it fills (at most) all pairs once
+  // 4-CTA clusters (two pairs sharing the W tile) when the device places enough of them and there are at least two
+  // row blocks; else lone pairs
+  const int quads = want_cp == 2 ? p16_max_quads() : 0;
+  const int cp = (quads >= 8 && m_tiles >= 2) ? 2 : 1;
+  const int units = cp == 2 ? quads : sm_count() / 2;            // clusters that run concurrently
+  const int items = ((m_tiles + cp - 1) / cp) * n_tiles;
+  P16Params p{M, N, K, bias, uint32_t(dtype), items, 0, items, g_p16_trace};
+  const int rem = items % units;
+  if (split_tail && items > units && rem != 0) {
+    // split the last partial wave so that it fills (at most) all clusters once
     int s = 0;
-    while (s < 2 && (rem << (s + 1)) <= max_pairs) ++s;
+    while (s < 2 && (rem << (s + 1)) <= units) ++s;
     if (s > 0) {
-      p.full_tiles = tiles - rem;
+      p.full_tiles = items - rem;
       p.tail_split_log2 = s;
+      p.total_items = p.full_tiles + (rem << s);
     }
   }
-  const int total = p.full_tiles + ((tiles - p.full_tiles) << p.tail_split_log2);
   CUtensorMap ta, tw, twt, to;
   MMR_TRY(make_tmap_2d(&ta, A16, M, K, lda, kCtaRows, dtype));
-  MMR_TRY(make_tmap_2d(&tw, W16, N, K, ldw, kBN / 2, dtype));
-  MMR_TRY(make_tmap_2d(&twt, W16, N, K, ldw, (kBN >> p.tail_split_log2) / 2, dtype));
+  MMR_TRY(make_tmap_2d(&tw, W16, N, K, ldw, kBN / 2 / cp, dtype));
+  MMR_TRY(make_tmap_2d(&twt, W16, N, K, ldw, (kBN >> p.tail_split_log2) / 2 / cp, dtype));
   MMR_TRY(make_tmap_ex(&to, out16, M, N, ldo16, dtype == MMR_DT_BF16 ? 1 : 0, 32, 32, 64));
-  const int grid = 2 * (total < max_pairs ? total : max_pairs);
-  if (dtype == MMR_DT_BF16) return dispatch_p16<BF16>(act, ta, tw, twt, to, p, grid, stream);
-  return dispatch_p16<FP16>(act, ta, tw, twt, to, p, grid, stream);
+  const int grid = 2 * cp * (p.total_items < units ? p.total_items : units);
+  if (dtype == MMR_DT_BF16) return dispatch_p16<BF16>(act, ta, tw, twt, to, p, grid, cp, stream);
+  return dispatch_p16<FP16>(act, ta, tw, twt, to, p, grid, cp, stream);
 }
 
 }  // namespace mmr
+
+/* Debug only (not in the public header): device buffer of [pairs][128] uint64 ns stamps, or null. */
+extern "C" void mmr_debug_set_p16_trace(unsigned long long* dev_buf) { mmr::g_p16_trace = dev_buf; }

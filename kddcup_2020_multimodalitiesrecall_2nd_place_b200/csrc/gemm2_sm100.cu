@@ -54,7 +54,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int k_blocks = p.K / kBK;
   const int total_tiles = m_tiles * n_tiles;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kEpiWarps && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_w);
     for (int s = 0; s < kPairStages; ++s) {
@@ -67,7 +67,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == kEpiWarps + 1) {
     tmem_alloc_2sm(tmem_slot, kTmemCols);
     tmem_relinquish_2sm();
   }
@@ -76,9 +76,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   cluster_sync_all();   // the peer's barriers are initialised before any remote arrive / TMA credit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                 // the previous kernel's outputs (this one's operands / residual) are complete
+  pdl_launch_dependents();    // the next kernel may be scheduled as soon as SMs free up
 
-  if (warp == 0) {
-    // ===================== TMA producer (both CTAs) =====================
+  if (warp == kEpiWarps) {
+    // ===================== TMA producer (both CTAs); warps 8 / 9: the arbiter favours higher warp ids =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -96,7 +98,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kEpiWarps + 1) {
     // ===================== MMA issuer (leader CTA, one thread) =====================
     if (rank == 0 && lane == 0) {
       const uint32_t idesc = umma_idesc_f16(p.idesc_fmt, kPairBM, kBN);
@@ -126,7 +128,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else {
     // ===================== epilogue warps (both CTAs, own 128 rows) =====================
-    const int ew = warp - 2;
+    const int ew = warp;
     const int quarter = warp & 3;
     const int half = ew >> 2;
     int it = 0;
@@ -148,7 +150,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();   // no CTA leaves while its peer may still read its smem or signal its barriers
-  if (warp == 1) {
+  if (warp == kEpiWarps + 1) {
     tc_fence_after();
     tmem_dealloc_2sm(tmem_base, kTmemCols);
   }
@@ -163,8 +165,7 @@ static mmr_status launch_pair(const CUtensorMap& ta, const CUtensorMap& tw, cons
     MMR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kPairSmemBytes)));
     configured = true;
   }
-  kern<<<grid, kGemmThreads, kPairSmemBytes, stream>>>(ta, tw, p);
-  MMR_CUDA_OK(cudaGetLastError());
+  MMR_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(kGemmThreads), kPairSmemBytes, stream, ta, tw, p));
   return MMR_OK;
 }
 

@@ -73,6 +73,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                 // the previous kernel's outputs (this one's operands / residual) are complete
+  pdl_launch_dependents();    // the next kernel may be scheduled as soon as SMs free up
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -241,8 +243,7 @@ static mmr_status launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, cons
     MMR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
     configured = true;
   }
-  kern<<<grid, kThreads, kSmemBytes, stream>>>(ta, tw, p);
-  MMR_CUDA_OK(cudaGetLastError());
+  MMR_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(kThreads), kSmemBytes, stream, ta, tw, p));
   return MMR_OK;
 }
 
@@ -280,10 +281,7 @@ mmr_status gemm(const void* A16, int64_t lda, const void* W16, int64_t ldw, int 
   MMR_REQUIRE(!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "mmr_gemm: bias must be 16-byte aligned");
   MMR_REQUIRE(dtype == MMR_DT_BF16 || dtype == MMR_DT_FP16, "mmr_gemm: bad dtype %d", dtype);
 
-  static const bool pair_enabled = [] {
-    const char* e = getenv("MMR_GEMM_PAIR");   // MMR_GEMM_PAIR=0 forces the single-CTA kernel (A/B measurements)
-    return !(e && e[0] == '0');
-  }();
+  const bool pair_enabled = tuning(MMR_TUNE_GEMM_PAIR) != 0;
   if (pair_enabled && gemm_pair16_eligible(M, N, K, residual, out16, out32))
     return gemm_pair16(A16, lda, W16, ldw, M, N, K, bias, out16, ldo16, act, dtype, stream);
   if (pair_enabled && gemm_pair_eligible(M, N, K)) {

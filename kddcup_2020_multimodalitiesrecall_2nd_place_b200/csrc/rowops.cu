@@ -1,6 +1,7 @@
 // Row-wise HBM-bound kernels: LayerNorm and the fp32 -> 16-bit cast of the region features.
 // One warp per row, 16-byte vector loads/stores, statistics in fp32 registers (two-pass over registers).
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace mmr {
 
@@ -13,6 +14,8 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, int M, int H, typename E16::T* __restrict__ out16,
                  int64_t ldo16, float* __restrict__ out32, int64_t ldo32, float scale, int accumulate) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int warps_per_block = blockDim.x >> 5;
   const int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -70,6 +73,8 @@ layernorm_kernel(const float* __restrict__ x, int64_t ldx, const float* __restri
 template <class E16>
 __global__ void __launch_bounds__(256)
 cast16_kernel(const float4* __restrict__ x, uint4* __restrict__ out, int64_t n8) {
+  pdl_wait();
+  pdl_launch_dependents();
   int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
   for (; i < n8; i += stride) {
@@ -98,11 +103,11 @@ mmr_status layernorm(const float* x, int64_t ldx, const float* gamma, const floa
   const int wpb = 8;
   const int grid = (M + wpb - 1) / wpb;
   if (dtype == MMR_DT_BF16) {
-    layernorm_kernel<BF16><<<grid, wpb * 32, 0, stream>>>(x, ldx, gamma, beta, eps, M, H,
+    (void)launch_pdl(layernorm_kernel<BF16>, dim3(grid), dim3(wpb * 32), 0, stream, x, ldx, gamma, beta, eps, M, H,
                                                           static_cast<BF16::T*>(out16), ldo16, out32, ldo32,
                                                           scale, accumulate);
   } else if (dtype == MMR_DT_FP16) {
-    layernorm_kernel<FP16><<<grid, wpb * 32, 0, stream>>>(x, ldx, gamma, beta, eps, M, H,
+    (void)launch_pdl(layernorm_kernel<FP16>, dim3(grid), dim3(wpb * 32), 0, stream, x, ldx, gamma, beta, eps, M, H,
                                                           static_cast<FP16::T*>(out16), ldo16, out32, ldo32,
                                                           scale, accumulate);
   } else {
@@ -122,10 +127,10 @@ mmr_status cast16(const float* x, void* out16, int64_t n, int dtype, cudaStream_
   int grid = int((n8 + 255) / 256);
   if (grid > 148 * 16) grid = 148 * 16;
   if (dtype == MMR_DT_BF16) {
-    cast16_kernel<BF16><<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(x),
+    (void)launch_pdl(cast16_kernel<BF16>, dim3(grid), dim3(256), 0, stream, reinterpret_cast<const float4*>(x),
                                                   reinterpret_cast<uint4*>(out16), n8);
   } else if (dtype == MMR_DT_FP16) {
-    cast16_kernel<FP16><<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(x),
+    (void)launch_pdl(cast16_kernel<FP16>, dim3(grid), dim3(256), 0, stream, reinterpret_cast<const float4*>(x),
                                                   reinterpret_cast<uint4*>(out16), n8);
   } else {
     return fail(MMR_ERR_INVALID, "mmr_cast16: bad dtype %d", dtype);

@@ -191,3 +191,31 @@ def test_fused_gemm_layernorm(M, K):
     # every row is normalised: mean ~ beta-weighted, but the pre-affine statistics must be exact
     z = (x32 - be) / g
     assert z.mean(1).abs().max().item() < 1e-4 and (z.var(1, unbiased=False) - 1).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("knob,value", [("TUNE_GEMM_CLUSTER", 2), ("TUNE_GEMM_TAIL", 0), ("TUNE_GEMM_P16", 0),
+                                        ("TUNE_GEMM_PAIR", 0), ("TUNE_GEMM_LN", 0), ("TUNE_PDL", 0)])
+def test_alternate_kernel_paths_agree(knob, value):
+    """Every kernel-selection knob (mmr_set_tuning) selects a path that computes the same thing: 4-CTA clusters with
+    TMA-multicast W (odd and even row-block counts), unsplit tail, the general pair kernel, the single-CTA kernel,
+    and GEMM + separate LayerNorm."""
+    from kddcup_2020_multimodalitiesrecall_2nd_place_b200 import ops, _lib
+    lib = _lib.load()
+    k = getattr(_lib, knob)
+    default = {"TUNE_GEMM_CLUSTER": 1}.get(knob, 1)
+    torch.manual_seed(5)
+    try:
+        _lib.check(lib.mmr_set_tuning(k, value))
+        for (M, N, K, act) in [(17408, 2304, 768, 0), (19200, 3072, 768, 2), (700, 512, 128, 1)]:
+            a = torch.randn(M, K, device="cuda").half()
+            w = (torch.randn(N, K, device="cuda") * 0.05).half()
+            b = torch.randn(N, device="cuda") * 0.1
+            o16, _ = ops.gemm(a, w, b, None, act=act, want16=True, want32=False)
+            torch.cuda.synchronize()
+            ref = a.float() @ w.float().t() + b
+            ref = {0: lambda x: x, 1: F.relu, 2: lambda x: F.gelu(x, approximate="tanh")}[act](ref)
+            assert _rel(o16, ref) < 6e-4, (knob, M, N, K)
+        if knob == "TUNE_GEMM_LN":
+            assert not lib.mmr_gemm_layernorm_supported(17408, 768, _lib.DT_FP16)
+    finally:
+        _lib.check(lib.mmr_set_tuning(k, default))
