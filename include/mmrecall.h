@@ -62,9 +62,11 @@ int mmr_abi_version(void);
  *   MMR_TUNE_GEMM_CLUSTER  (env MMR_GEMM_CLUSTER, default 1) 1 = lone CTA pairs, 2 = 4-CTA clusters sharing W by
  *                                                            TMA multicast (measured slower: 132 of 148 SMs)
  *   MMR_TUNE_GEMM_LN       (env MMR_GEMM_LN,      default 1) fused projection + residual + LayerNorm kernel
- *   MMR_TUNE_PDL           (env MMR_PDL,          default 1) programmatic dependent launch between the kernels */
+ *   MMR_TUNE_PDL           (env MMR_PDL,          default 1) programmatic dependent launch between the kernels
+ *   MMR_TUNE_ATTN_TMA      (env MMR_ATTN_TMA,     default 0) persistent TMA-pipelined mma.sync attention kernel
+ *                                                            (measured slower than one CTA per (pair, head): 40 vs 32 us) */
 enum { MMR_TUNE_GEMM_PAIR = 0, MMR_TUNE_GEMM_P16 = 1, MMR_TUNE_GEMM_TAIL = 2, MMR_TUNE_GEMM_CLUSTER = 3,
-       MMR_TUNE_GEMM_LN = 4, MMR_TUNE_PDL = 5, MMR_TUNE_COUNT = 6 };
+       MMR_TUNE_GEMM_LN = 4, MMR_TUNE_PDL = 5, MMR_TUNE_ATTN_TMA = 6, MMR_TUNE_COUNT = 7 };
 mmr_status mmr_set_tuning(int knob, int value);
 /* MMR_OK iff `device` is an sm_100 part. */
 mmr_status mmr_device_check(int device);

@@ -118,13 +118,24 @@ def test_layernorm():
         assert _rel(acc, 1.0 + ref / 3.0) < 1e-6
 
 
+@pytest.mark.parametrize("tma", [1, 0])
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-def test_attention(dtype):
-    from kddcup_2020_multimodalitiesrecall_2nd_place_b200 import ops
+def test_attention(dtype, tma):
+    """Both attention kernels: the persistent TMA-pipelined one (default) and the one-CTA-per-(pair, head) one."""
+    from kddcup_2020_multimodalitiesrecall_2nd_place_b200 import ops, _lib
+    _lib.check(_lib.load().mmr_set_tuning(_lib.TUNE_ATTN_TMA, tma))
+    try:
+        _attention_cases(dtype, ops)
+    finally:
+        _lib.check(_lib.load().mmr_set_tuning(_lib.TUNE_ATTN_TMA, 0))
+
+
+def _attention_cases(dtype, ops):
     torch.manual_seed(2)
     H = 12
     for (B, Sq, Sk, masked) in [(3, 68, 68, True), (2, 32, 36, True), (2, 36, 32, False), (2, 104, 104, False),
-                                (1, 128, 128, True), (2, 10, 23, True), (2, 1, 1, False), (2, 28, 28, True)]:
+                                (1, 128, 128, True), (2, 10, 23, True), (2, 1, 1, False), (2, 28, 28, True),
+                                (256, 68, 68, True), (300, 36, 32, True)]:
         qkv_q = torch.randn(B * Sq, 3 * 768, device="cuda").to(dtype)
         qkv_k = qkv_q if Sq == Sk else torch.randn(B * Sk, 3 * 768, device="cuda").to(dtype)
         mask = None
