@@ -31,14 +31,26 @@ namespace mmr {
 
 constexpr int kLnN = 768;
 constexpr int kLnTiles = kLnN / kBN;            // 3 column tiles = 3 pairs per group
-constexpr int kLnStages = 4;
 // the warp arbiter favours higher warp ids: the two latency-critical single-thread roles get ids 8 and 9
 constexpr int kLnProducerWarp = kEpiWarps, kLnMmaWarp = kEpiWarps + 1;
+// Shared-memory split between the operand ring and the epilogue, per K:
+//   K <= 1024 (out-projection): the launch is bound by its epilogue (tools/ln_trace.py), so 3 operand stages and a
+//     3-slot residual / fp32-staging ring + 1 16-bit stage per warp (what fits beside them): three of the four residual chunks of a tile are
+//     in flight before the accumulator is even complete;
+//   larger K (FFN-out): MMA-bound, 4 operand stages, 2 slots + 1 16-bit stage per warp.
+template <int STAGES, int SLOTS, int O16>
+struct LnCfg {
+  static constexpr int kStages = STAGES, kSlots = SLOTS, kO16 = O16;
+  static constexpr int kWarpBytes = SLOTS * 4096 + O16 * 2048;
+  // bulk store groups are committed per chunk as {16-bit}, {fp32}: this many of the most recent may still be reading
+  // their buffers when the next chunk starts writing (slot reuse distance SLOTS, 16-bit stage reuse distance O16)
+  static constexpr int kPending = (2 * SLOTS - 2) < (2 * O16 - 1) ? (2 * SLOTS - 2) : (2 * O16 - 1);
+  static constexpr size_t kSmemBytes =
+      1024 + PairRing<STAGES>::kOperandBytes + size_t(kEpiWarps) * kWarpBytes + 3 * kBN * 4 + 512;
+};
+using LnCfgShortK = LnCfg<3, 3, 1>;
+using LnCfgLongK = LnCfg<4, 2, 1>;
 constexpr int kLnSlots = 2 * kLnTiles;          // partial statistics per row: 3 column tiles x 2 halves
-constexpr int kLnWarpBytes = 2 * 4096 + 2048;       // per epilogue warp: two fp32 slots + one 16-bit stage
-constexpr int kLnVecBytes = 3 * kBN * 4;            // bias / gamma / beta of this pair's 256 columns
-constexpr size_t kLnSmemBytes =
-    1024 + PairRing<kLnStages>::kOperandBytes + size_t(kEpiWarps) * kLnWarpBytes + kLnVecBytes + 512;
 
 struct GemmLnParams {
   int M, K;
@@ -46,9 +58,8 @@ struct GemmLnParams {
   const float* gamma;     // [768]
   const float* beta;      // [768]
   float eps;
-  float2* stats;          // [m_tiles][6][256]  (mean_i, M2_i) partials
-  uint32_t* counters;     // [m_tiles][2][4] arrivals per (row block, CTA rank, 32-row quarter); zero between launches
-  uint32_t* done;         // CTAs finished (the last one re-zeroes the counters)
+  uint4* stats;           // [m_tiles][6][256]  {mean_i, tag, M2_i, tag}: each half is one 8-byte store carrying its flag
+  uint32_t* epoch;        // [0] tag of this launch (read at kernel start), [1] CTAs finished; the last CTA bumps [0]
   uint32_t idesc_fmt;
   unsigned long long* trace;   // debug: per (CTA, epilogue warp, tile) phase timestamps in ns, or null
 };
@@ -64,20 +75,21 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
       p.trace[((size_t(blockIdx.x) * kEpiWarps + ew) * 4 + it) * 8 + (k)] = globaltimer_ns();        \
   } while (0)
 
-template <class E16>
+template <class E16, class CFG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                const __grid_constant__ CUtensorMap tmap_r, const __grid_constant__ CUtensorMap tmap_o32,
                const __grid_constant__ CUtensorMap tmap_o16, const GemmLnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kLnStages = CFG::kStages, kSlots = CFG::kSlots, kO16 = CFG::kO16;
   uint8_t* epi = smem + PairRing<kLnStages>::kOperandBytes;                       // 1024-aligned
-  float* vec_s = reinterpret_cast<float*>(epi + size_t(kEpiWarps) * kLnWarpBytes);   // [3][256]: bias, gamma, beta
+  float* vec_s = reinterpret_cast<float*>(epi + size_t(kEpiWarps) * CFG::kWarpBytes);   // [3][256]: bias, gamma, beta
   uint64_t* bars = reinterpret_cast<uint64_t*>(vec_s + 3 * kBN);
   PairRing<kLnStages> ring;
   ring.carve(smem, bars);
-  uint64_t* res_bar = bars + PairRing<kLnStages>::kNumBars;    // [8 warps][2 slots] residual chunk landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * kEpiWarps);
+  uint64_t* res_bar = bars + PairRing<kLnStages>::kNumBars;    // [8 warps][kSlots] residual chunk landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + kSlots * kEpiWarps);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -96,7 +108,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tma_prefetch_desc(&tmap_o32);
     tma_prefetch_desc(&tmap_o16);
     ring.init(2 * kEpiWarps);
-    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
+    for (int i = 0; i < kSlots * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == kLnMmaWarp) {
@@ -113,7 +125,8 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();                 // the previous kernel's outputs (this one's operands / residual) are complete
+  pdl_wait();
+  const uint32_t tag_of_launch = *reinterpret_cast<const volatile uint32_t*>(p.epoch);                 // the previous kernel's outputs (this one's operands / residual) are complete
   pdl_launch_dependents();    // the next kernel may be scheduled as soon as SMs free up
 
   if (warp == kLnProducerWarp) {
@@ -142,20 +155,20 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int ew = warp;                   // epilogue warps are warps 0..7
     const int quarter = warp & 3;
     const int half = ew >> 2;
-    uint8_t* wbuf = epi + size_t(ew) * kLnWarpBytes;
-    // wbuf + 4096 s: fp32 slot s   [32 rows x 32 cols], 128-byte swizzle
-    // wbuf + 8192  : 16-bit stage [32 rows x 32 cols], 64-byte swizzle
-    uint8_t* o16_s = wbuf + 8192;
+    uint8_t* wbuf = epi + size_t(ew) * CFG::kWarpBytes;
+    // wbuf + 4096 s               : fp32 slot s    [32 rows x 32 cols], 128-byte swizzle
+    // wbuf + 4096 kSlots + 2048 t : 16-bit stage t [32 rows x 32 cols], 64-byte swizzle
     const float* bias_w = vec_s + half * 128;             // this warp's 128 columns of the three vectors
     const float* gamma_w = vec_s + kBN + half * 128;
     const float* beta_w = vec_s + 2 * kBN + half * 128;
-    uint64_t* rfull = res_bar + 2 * ew;
+    uint64_t* rfull = res_bar + kSlots * ew;
+    const uint32_t tag = tag_of_launch;   // this launch's flag value (never 0)
     const uint32_t tempty_leader0 = mapa_u32(smem_u32(&ring.tempty[0]), 0);
     const uint32_t tempty_leader1 = mapa_u32(smem_u32(&ring.tempty[1]), 0);
     const int col_w = n_tile * kBN + half * 128;            // first of this warp's 128 columns
     const int row_in_blk = int(rank) * kCtaRows + quarter * 32;
     const uint32_t sw128 = uint32_t(lane & 7), sw64 = uint32_t((lane >> 1) & 3);
-    uint32_t rph = 0;                                       // parity bits of the two residual barriers
+    uint32_t rph = 0;                                       // parity bits of the residual barriers
     int it = 0;
     for (int m_blk = group; m_blk < m_tiles; m_blk += n_groups, ++it) {
       const int acc = it & 1;
@@ -163,11 +176,11 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const uint32_t taddr = tmem_base + uint32_t(acc) * kBN + (uint32_t(quarter * 32) << 16) + uint32_t(half * 128);
 
       MMR_LN_STAMP(0);
-      // residual chunks 0 and 1 -> slots (the previous block's stores must have finished reading them)
+      // the first residual chunks -> slots (the previous block's stores must have finished reading them)
       if (lane == 0) {
         bulk_wait_read<0>();
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < kSlots; ++s) {
           mbar_arrive_expect_tx(&rfull[s], 4096);
           tma_load_2d(wbuf + 4096 * s, &tmap_r, &rfull[s], col_w + 32 * s, row0);
         }
@@ -180,7 +193,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       float shift = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
-        const int s = c & 1;
+        const int s = c % kSlots;
         uint8_t* slot_s = wbuf + 4096 * s;
         mbar_wait(&rfull[s], (rph >> s) & 1u);
         rph ^= 1u << s;
@@ -202,9 +215,9 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         tmem_st_32x32(taddr + uint32_t(c * 32), v);
         __syncwarp();   // every lane has read its slot row
-        if (lane == 0 && c < 2) {
+        if (lane == 0 && c + kSlots < 4) {
           mbar_arrive_expect_tx(&rfull[s], 4096);
-          tma_load_2d(slot_s, &tmap_r, &rfull[s], col_w + 32 * (c + 2), row0);
+          tma_load_2d(slot_s, &tmap_r, &rfull[s], col_w + 32 * (c + kSlots), row0);
         }
       }
       tmem_st_wait();
@@ -215,28 +228,29 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       {
         const float mean_i = shift + s1 * (1.0f / 128.0f);
         const float m2_i = fmaxf(s2 - s1 * s1 * (1.0f / 128.0f), 0.f);
-        float2* tab = p.stats + size_t(m_blk) * kLnSlots * kPairRows + row_in_blk + lane;
-        tab[size_t(n_tile * 2 + half) * kPairRows] = make_float2(mean_i, m2_i);
-        __threadfence();
-        __syncwarp();
-        uint32_t* ctr = p.counters + (m_blk * 2 + int(rank)) * 4 + quarter;
-        if (lane == 0) {
-          atomicAdd(ctr, 1u);
-          uint32_t spins = 0;
-          while (ld_relaxed_gpu_u32(ctr) < uint32_t(kLnSlots)) {   // relaxed polls: no L1 invalidation per probe
-            if (++spins > MMR_SPIN_LIMIT) __trap();
-          }
-          fence_acq_rel_gpu();                                      // one acquire for the partials read below
+        // Each half of an entry is ONE 8-byte store {value, tag}: a reader that sees this launch's tag sees the value
+        // (no fence, no atomic, no counter).  Every lane polls the 6 entries of its own row.
+        uint4* tab = p.stats + size_t(m_blk) * kLnSlots * kPairRows + row_in_blk + lane;
+        {
+          uint8_t* mine = reinterpret_cast<uint8_t*>(tab + size_t(n_tile * 2 + half) * kPairRows);
+          st_volatile_u32x2(mine, __float_as_uint(mean_i), tag);
+          st_volatile_u32x2(mine + 8, __float_as_uint(m2_i), tag);
         }
-        __syncwarp();
         float means[kLnSlots], m2_tot = 0.f;
         mean = 0.f;
 #pragma unroll
         for (int s = 0; s < kLnSlots; ++s) {
-          const float2 q = __ldcg(tab + size_t(s) * kPairRows);
-          means[s] = q.x;
-          mean += q.x;
-          m2_tot += q.y;
+          const uint8_t* e = reinterpret_cast<const uint8_t*>(tab + size_t(s) * kPairRows);
+          uint2 a = ld_volatile_u32x2(e), b = ld_volatile_u32x2(e + 8);
+          uint32_t spins = 0;
+          while (a.y != tag || b.y != tag) {
+            if (++spins > MMR_SPIN_LIMIT) __trap();
+            a = ld_volatile_u32x2(e);
+            b = ld_volatile_u32x2(e + 8);
+          }
+          means[s] = __uint_as_float(a.x);
+          mean += means[s];
+          m2_tot += __uint_as_float(b.x);
         }
         mean *= (1.0f / kLnSlots);
 #pragma unroll
@@ -251,12 +265,10 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       // ---- pass 2: normalise from TMEM, affine, swizzled stages, TMA stores
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
-        const int s = c & 1;
-        uint8_t* slot_s = wbuf + 4096 * s;
+        uint8_t* slot_s = wbuf + 4096 * (c % kSlots);
+        uint8_t* o16_s = wbuf + 4096 * kSlots + 2048 * (c % kO16);
         const int col0 = col_w + c * 32;
-        // Bulk groups are committed per chunk as {16-bit store}, {fp32 store}; "at most one pending" therefore means
-        // the previous chunk's 16-bit store and the fp32 store of two chunks ago have read their buffers.
-        if (lane == 0) bulk_wait_read<1>();
+        if (lane == 0) bulk_wait_read<CFG::kPending>();   // this chunk's slot and 16-bit stage have been read
         __syncwarp();
         uint32_t v[32];
         tmem_ld_32x32(taddr + uint32_t(c * 32), v);
@@ -306,23 +318,24 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tc_fence_after();
     tmem_dealloc_2sm(tmem_base, kTmemCols);
   }
-  // The last CTA to finish zeroes the arrival counters for the next launch (nobody can still be polling them).
+  // The last CTA to finish moves the tag on for the next launch (nobody can still be polling with the old one).
   if (threadIdx.x == 0) {
     __threadfence();
-    if (atomicAdd(p.done, 1u) == gridDim.x - 1) {
-      for (int i = 0; i < m_tiles * 8; ++i) p.counters[i] = 0;
-      *p.done = 0;
+    if (atomicAdd(p.epoch + 1, 1u) == gridDim.x - 1) {
+      p.epoch[1] = 0;
+      const uint32_t next = tag_of_launch + 1u;
+      p.epoch[0] = next == 0u ? 1u : next;
       __threadfence();
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-// Exchange table + counters, one per device, grown on demand (mmr_create reserves it for max_batch so that no
+// Exchange table + launch tag, one per device, grown on demand (mmr_create reserves it for max_batch so that no
 // allocation happens inside mmr_forward).  One fused GEMM+LN may be in flight per device at a time.
 struct LnWorkspace {
-  float2* stats = nullptr;
-  uint32_t* counters = nullptr;
+  uint4* stats = nullptr;
+  uint32_t* epoch = nullptr;
   int m_tiles = 0;
 };
 static LnWorkspace g_ln_ws[16];
@@ -337,30 +350,33 @@ mmr_status gemm_ln_reserve(int M) {
   if (m_tiles <= ws.m_tiles) return MMR_OK;
   MMR_CUDA_OK(cudaDeviceSynchronize());   // a kernel may still use the old table
   if (ws.stats) cudaFree(ws.stats);
-  if (ws.counters) cudaFree(ws.counters);
+  if (ws.epoch) cudaFree(ws.epoch);
   ws = LnWorkspace();
-  MMR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&ws.stats), size_t(m_tiles) * kLnSlots * kPairRows * sizeof(float2)));
-  MMR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&ws.counters), (size_t(m_tiles) * 8 + 1) * sizeof(uint32_t)));
-  MMR_CUDA_OK(cudaMemset(ws.counters, 0, (size_t(m_tiles) * 8 + 1) * sizeof(uint32_t)));
+  const size_t bytes = size_t(m_tiles) * kLnSlots * kPairRows * sizeof(uint4);
+  MMR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&ws.stats), bytes));
+  MMR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&ws.epoch), 2 * sizeof(uint32_t)));
+  MMR_CUDA_OK(cudaMemset(ws.stats, 0, bytes));               // tag 0 = "never written"
+  const uint32_t init[2] = {1u, 0u};
+  MMR_CUDA_OK(cudaMemcpy(ws.epoch, init, sizeof(init), cudaMemcpyHostToDevice));
   MMR_CUDA_OK(cudaDeviceSynchronize());
   ws.m_tiles = m_tiles;
   return MMR_OK;
 }
 
 // Largest number of co-resident CTA pairs of this kernel (0 when the device cannot place one): queried once.
-template <class E16>
+template <class E16, class CFG>
 static int ln_max_pairs() {
   static int cached = -1;
   if (cached >= 0) return cached;
-  auto kern = gemm_ln_kernel<E16>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLnSmemBytes)) != cudaSuccess) {
+  auto kern = gemm_ln_kernel<E16, CFG>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(CFG::kSmemBytes)) != cudaSuccess) {
     cudaGetLastError();
     return cached = 0;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * 74, 1, 1);
   cfg.blockDim = dim3(kGemmThreads, 1, 1);
-  cfg.dynamicSmemBytes = kLnSmemBytes;
+  cfg.dynamicSmemBytes = CFG::kSmemBytes;
   cudaLaunchAttribute attr;
   attr.id = cudaLaunchAttributeClusterDimension;
   attr.val.clusterDim.x = 2;
@@ -375,21 +391,32 @@ static int ln_max_pairs() {
   }
   return cached = n;
 }
+template <class E16>
+static int ln_max_pairs_for(int K) {
+  return K <= 1024 ? ln_max_pairs<E16, LnCfgShortK>() : ln_max_pairs<E16, LnCfgLongK>();
+}
 
 bool gemm_ln_eligible(int M, int N, int K, int dtype) {
   if (tuning(MMR_TUNE_GEMM_LN) == 0 || N != kLnN || M <= kCtaRows || K % kBK != 0) return false;
-  return (dtype == MMR_DT_BF16 ? ln_max_pairs<BF16>() : ln_max_pairs<FP16>()) >= kLnTiles;
+  return (dtype == MMR_DT_BF16 ? ln_max_pairs_for<BF16>(K) : ln_max_pairs_for<FP16>(K)) >= kLnTiles;
 }
 
+template <class E16, class CFG>
+static mmr_status launch_ln_cfg(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tr,
+                                const CUtensorMap& to32, const CUtensorMap& to16, const GemmLnParams& p,
+                                cudaStream_t stream) {
+  const int m_tiles = (p.M + kPairRows - 1) / kPairRows;
+  const int max_groups = ln_max_pairs<E16, CFG>() / kLnTiles;
+  const int groups = m_tiles < max_groups ? m_tiles : max_groups;
+  MMR_CUDA_OK(launch_pdl(gemm_ln_kernel<E16, CFG>, dim3(2 * kLnTiles * groups), dim3(kGemmThreads), CFG::kSmemBytes,
+                         stream, ta, tw, tr, to32, to16, p));
+  return MMR_OK;
+}
 template <class E16>
 static mmr_status launch_ln(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tr, const CUtensorMap& to32,
                             const CUtensorMap& to16, const GemmLnParams& p, cudaStream_t stream) {
-  const int m_tiles = (p.M + kPairRows - 1) / kPairRows;
-  const int max_groups = ln_max_pairs<E16>() / kLnTiles;
-  const int groups = m_tiles < max_groups ? m_tiles : max_groups;
-  MMR_CUDA_OK(launch_pdl(gemm_ln_kernel<E16>, dim3(2 * kLnTiles * groups), dim3(kGemmThreads), kLnSmemBytes, stream, ta, tw,
-                         tr, to32, to16, p));
-  return MMR_OK;
+  if (p.K <= 1024) return launch_ln_cfg<E16, LnCfgShortK>(ta, tw, tr, to32, to16, p, stream);
+  return launch_ln_cfg<E16, LnCfgLongK>(ta, tw, tr, to32, to16, p, stream);
 }
 
 mmr_status gemm_ln(const void* A16, int64_t lda, const void* W16, int64_t ldw, int M, int K, const float* bias,
@@ -415,7 +442,7 @@ mmr_status gemm_ln(const void* A16, int64_t lda, const void* W16, int64_t ldw, i
   MMR_TRY(make_tmap_ex(&to32, out32, M, kLnN, ldo32, 2, 32, 32, 128));
   MMR_TRY(make_tmap_ex(&to16, out16, M, kLnN, ldo16, ek, 32, 32, 64));
   const LnWorkspace& ws = g_ln_ws[dev];
-  GemmLnParams p{M, K, bias, gamma, beta, eps, ws.stats, ws.counters, ws.counters + size_t(ws.m_tiles) * 8, uint32_t(dtype), g_ln_trace};
+  GemmLnParams p{M, K, bias, gamma, beta, eps, ws.stats, ws.epoch, uint32_t(dtype), g_ln_trace};
   if (dtype == MMR_DT_BF16) return launch_ln<BF16>(ta, tw, tr, to32, to16, p, stream);
   return launch_ln<FP16>(ta, tw, tr, to32, to16, p, stream);
 }
