@@ -64,9 +64,11 @@ int mmr_abi_version(void);
  *   MMR_TUNE_GEMM_LN       (env MMR_GEMM_LN,      default 1) fused projection + residual + LayerNorm kernel
  *   MMR_TUNE_PDL           (env MMR_PDL,          default 1) programmatic dependent launch between the kernels
  *   MMR_TUNE_ATTN_TMA      (env MMR_ATTN_TMA,     default 0) persistent TMA-pipelined mma.sync attention kernel
- *                                                            (measured slower than one CTA per (pair, head): 40 vs 32 us) */
+ *                                                            (measured slower than one CTA per (pair, head): 40 vs 32 us)
+ *   MMR_TUNE_ATTN_TC       (env MMR_ATTN_TC,      default 0) tcgen05 / TMEM attention kernel (attention_tc.cu): correct,
+ *                                                            40.9 us vs 32.5 us at B=256, S=68 (one item in flight per CTA) */
 enum { MMR_TUNE_GEMM_PAIR = 0, MMR_TUNE_GEMM_P16 = 1, MMR_TUNE_GEMM_TAIL = 2, MMR_TUNE_GEMM_CLUSTER = 3,
-       MMR_TUNE_GEMM_LN = 4, MMR_TUNE_PDL = 5, MMR_TUNE_ATTN_TMA = 6, MMR_TUNE_COUNT = 7 };
+       MMR_TUNE_GEMM_LN = 4, MMR_TUNE_PDL = 5, MMR_TUNE_ATTN_TMA = 6, MMR_TUNE_ATTN_TC = 7, MMR_TUNE_COUNT = 8 };
 mmr_status mmr_set_tuning(int knob, int value);
 /* MMR_OK iff `device` is an sm_100 part. */
 mmr_status mmr_device_check(int device);

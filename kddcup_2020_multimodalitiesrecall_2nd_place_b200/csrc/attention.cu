@@ -11,6 +11,7 @@
 #include <algorithm>
 
 #include "gemm_common.cuh"
+#include "kernels.cuh"
 
 namespace mmr {
 
@@ -469,6 +470,8 @@ mmr_status attention(const void* q, int64_t ldq, const void* k, int64_t ldk, con
                   (reinterpret_cast<uintptr_t>(out16) & 3) == 0,
               "mmr_attention: q/k/v must be 16-byte aligned");
   MMR_REQUIRE(dtype == MMR_DT_BF16 || dtype == MMR_DT_FP16, "mmr_attention: bad dtype %d", dtype);
+  if (attention_tc_eligible(out16, ldo))
+    return attention_tc(q, ldq, k, ldk, v, ldv, key_mask, out16, ldo, B, Sq, Sk, heads, dtype, stream);
   // the TMA kernel needs out16 rows 16-byte aligned (vector stores) on top of the operand alignment checked above
   const bool tma_path = tuning(MMR_TUNE_ATTN_TMA) != 0 && ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out16) & 15) == 0;
 #define MMR_ATT(E, KT)                                                                                               \

@@ -13,6 +13,11 @@ mmr_status layernorm(const float* x, int64_t ldx, const float* gamma, const floa
 mmr_status attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                      const int32_t* key_mask, void* out16, int64_t ldo, int B, int Sq, int Sk, int heads,
                      int dtype, cudaStream_t stream);
+// tcgen05 / TMEM attention (attention_tc.cu); same contract as attention()
+bool attention_tc_eligible(const void* out16, int64_t ldo);
+mmr_status attention_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                        const int32_t* key_mask, void* out16, int64_t ldo, int B, int Sq, int Sk, int heads, int dtype,
+                        cudaStream_t stream);
 mmr_status cast16(const float* x, void* out16, int64_t n, int dtype, cudaStream_t stream);
 // out = LN(A . W^T + bias + residual) for N = 768 in one kernel (gemm_ln_sm100.cu); residual may alias out32.
 bool gemm_ln_eligible(int M, int N, int K, int dtype);

@@ -118,16 +118,20 @@ def test_layernorm():
         assert _rel(acc, 1.0 + ref / 3.0) < 1e-6
 
 
-@pytest.mark.parametrize("tma", [1, 0])
+@pytest.mark.parametrize("kernel", ["tcgen05", "mma_sync", "mma_sync_tma"])
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-def test_attention(dtype, tma):
-    """Both attention kernels: the persistent TMA-pipelined one (default) and the one-CTA-per-(pair, head) one."""
+def test_attention(dtype, kernel):
+    """All three attention kernels: one CTA per (pair, head) with mma.sync (default: fastest at these sizes), tcgen05 /
+    TMEM with warp-specialised softmax, and the persistent TMA-pipelined mma.sync variant."""
     from kddcup_2020_multimodalitiesrecall_2nd_place_b200 import ops, _lib
-    _lib.check(_lib.load().mmr_set_tuning(_lib.TUNE_ATTN_TMA, tma))
+    lib = _lib.load()
+    _lib.check(lib.mmr_set_tuning(_lib.TUNE_ATTN_TC, 1 if kernel == "tcgen05" else 0))
+    _lib.check(lib.mmr_set_tuning(_lib.TUNE_ATTN_TMA, 1 if kernel == "mma_sync_tma" else 0))
     try:
         _attention_cases(dtype, ops)
     finally:
-        _lib.check(_lib.load().mmr_set_tuning(_lib.TUNE_ATTN_TMA, 0))
+        _lib.check(lib.mmr_set_tuning(_lib.TUNE_ATTN_TC, 0))
+        _lib.check(lib.mmr_set_tuning(_lib.TUNE_ATTN_TMA, 0))
 
 
 def _attention_cases(dtype, ops):
