@@ -74,6 +74,35 @@ mmr_status mmr_set_tuning(int knob, int value);
 mmr_status mmr_device_check(int device);
 
 /* ------------------------------------------------------------------------------------------------
+ * Input decode (host code, no GPU): the per-line work of the reference loaders -- tab split, base64 decode of boxes /
+ * 2048-d features / class labels, zero padding to the box budget -- imagebert_zk/load_data_v4.py:133-163, 91-102,
+ * 380-383; lxmert/src/utils.py:23-36.  Lines are decoded by `n_threads` threads (<= 0: all cores) straight into the
+ * caller's batch arrays (use pinned memory to feed the scorer).  Tokenisation of `query` and of the class-label phrases
+ * stays with the caller (tokenizer.py); boxes come back RAW, normalisation /[h, w, h, w] (+ area) is mmr_boxes_normalize.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t max_boxes;      /* R: box slots per record (reference MAX_BOX_NUM = 10)                              */
+  int32_t feat_dim;       /* 2048                                                                              */
+  int64_t* product_id;    /* [n]                                                                               */
+  int32_t* image_h;       /* [n]                                                                               */
+  int32_t* image_w;       /* [n]                                                                               */
+  int32_t* num_boxes;     /* [n] as stored in the file (may exceed R; slots hold the first R)                  */
+  float* boxes4;          /* [n, R, 4] raw pixel boxes, zero padded                                            */
+  float* feats;           /* [n, R, feat_dim] fp32, zero padded                                                */
+  int64_t* class_labels;  /* [n, R] detector class ids, zero padded                                            */
+  int64_t* query_id;      /* [n]                                                                               */
+  int64_t* query_off;     /* [n, 2] (offset, length) of each query string inside query_text                    */
+  char* query_text;       /* concatenated UTF-8 query strings (order of arrival, not of lines)                 */
+  size_t query_cap;       /* capacity of query_text in bytes                                                   */
+} mmr_decode_out;
+mmr_status mmr_decode_tsv(const char* const* lines, const size_t* line_len, int64_t n_lines, const mmr_decode_out* out,
+                          int n_threads);
+/* boxes5[i, r] = (x1/h, y1/w, x2/h, y2/w, (x2-x1)(y2-y1)/(w h)) exactly as load_data_v4.py:142-145 divides
+ * (with_area != 0; zk) or the first four only (with_area == 0; lxmert utils.py:31).  Device pointers; fp32 division. */
+mmr_status mmr_boxes_normalize(const float* boxes4, const int32_t* image_h, const int32_t* image_w, int64_t n,
+                               int max_boxes, int with_area, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Operator level (one kernel each).  Used by the model driver below and by the parity tests.
  * ---------------------------------------------------------------------------------------------- */
 

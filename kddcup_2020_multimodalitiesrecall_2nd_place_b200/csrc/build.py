@@ -17,7 +17,7 @@ HERE = Path(__file__).resolve().parent
 PKG = HERE.parent
 LIB = PKG / "libmmrecall.so"
 OBJ_DIR = HERE / "build"
-SOURCES = ["common.cu", "gemm_sm100.cu", "gemm2_sm100.cu", "gemm16_sm100.cu", "gemm_ln_sm100.cu", "rowops.cu", "attention.cu", "attention_tc.cu", "embed.cu", "model.cu"]
+SOURCES = ["common.cu", "gemm_sm100.cu", "gemm2_sm100.cu", "gemm16_sm100.cu", "gemm_ln_sm100.cu", "rowops.cu", "attention.cu", "attention_tc.cu", "embed.cu", "model.cu", "decode.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -60,7 +60,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
     cmd = [NVCC, "-shared", "-o", str(LIB), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a",
-           "-lcudart"]
+           "-lcudart", "-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stderr}")

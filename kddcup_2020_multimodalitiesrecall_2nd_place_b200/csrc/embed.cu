@@ -500,3 +500,32 @@ extern "C" mmr_status mmr_linear_head(const float* x, int width, const float* ln
   MMR_REQUIRE((ln_gamma == nullptr) == (ln_beta == nullptr), "mmr_linear_head: give both LayerNorm vectors or none");
   return mmr::linear_head(x, width, ln_gamma, ln_beta, W, bias, B, probs, logits, static_cast<cudaStream_t>(stream));
 }
+
+// Box normalisation of the loaders (load_data_v4.py:142-145; lxmert utils.py:31) on the device.  The reference divides
+// float32 boxes by a Python list of ints, i.e. in float64, and stores float32: reproduced with double division.
+__global__ void boxes_normalize_kernel(const float* __restrict__ b4, const int32_t* __restrict__ hh,
+                                       const int32_t* __restrict__ ww, int64_t n_slots, int R, int with_area,
+                                       float* __restrict__ out) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_slots) return;
+  const int64_t rec = i / R;
+  const double h = double(hh[rec]), w = double(ww[rec]);
+  const float4 b = *reinterpret_cast<const float4*>(b4 + 4 * i);
+  const int od = with_area ? 5 : 4;
+  float* o = out + od * i;
+  o[0] = float(double(b.x) / h);
+  o[1] = float(double(b.y) / w);
+  o[2] = float(double(b.z) / h);
+  o[3] = float(double(b.w) / w);
+  if (with_area) o[4] = float(double((b.z - b.x) * (b.w - b.y)) / (w * h));
+}
+extern "C" mmr_status mmr_boxes_normalize(const float* boxes4, const int32_t* image_h, const int32_t* image_w, int64_t n,
+                                          int max_boxes, int with_area, float* out, void* stream) {
+  MMR_TRY(mmr::require_sm100());
+  MMR_REQUIRE(boxes4 && image_h && image_w && out && n > 0 && max_boxes > 0, "mmr_boxes_normalize: bad argument");
+  const int64_t slots = n * max_boxes;
+  boxes_normalize_kernel<<<unsigned((slots + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      boxes4, image_h, image_w, slots, max_boxes, with_area, out);
+  MMR_CUDA_OK(cudaGetLastError());
+  return MMR_OK;
+}

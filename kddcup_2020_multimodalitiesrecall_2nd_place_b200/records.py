@@ -1,0 +1,169 @@
+"""Record decode + batch assembly for the competition TSV files.
+
+`decode_lines` hands the raw lines to the multi-threaded C++ decoder (mmr_decode_tsv) which fills pinned batch arrays;
+`assemble_feeds` turns a decoded batch + a tokenizer + the class-label phrase map into the feed dict of a MatchScorer
+(the rest of `read_line` / `get_batch`: imagebert_zk/load_data_v4.py:133-163, 204, 264-265, 380-389;
+imagebert_lds/src/load_data_pred.py:94-121, 159; lxmert/src/utils.py:23-59).  Box normalisation runs on the GPU
+(mmr_boxes_normalize); everything else here is integer bookkeeping on the host.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import LDS, LXMERT, ZK, ModelConfig
+
+
+class _DecodeOut(C.Structure):
+    _fields_ = [("max_boxes", C.c_int32), ("feat_dim", C.c_int32), ("product_id", C.c_void_p), ("image_h", C.c_void_p),
+                ("image_w", C.c_void_p), ("num_boxes", C.c_void_p), ("boxes4", C.c_void_p), ("feats", C.c_void_p),
+                ("class_labels", C.c_void_p), ("query_id", C.c_void_p), ("query_off", C.c_void_p),
+                ("query_text", C.c_void_p), ("query_cap", C.c_size_t)]
+
+
+def _host(shape, dtype, pin):
+    t = torch.empty(shape, dtype=dtype)
+    return t.pin_memory() if pin and torch.cuda.is_available() else t
+
+
+class RecordDecoder:
+    """Reusable decode target: pinned batch arrays for up to `max_records` lines, allocated once (fresh pinned or
+    pageable memory costs more in page faults than the decode itself), filled by mmr_decode_tsv."""
+
+    def __init__(self, max_records: int, max_boxes: int = 10, feat_dim: int = 2048, n_threads: int = 0, pin: bool = True,
+                 max_query_bytes: int = 1024):
+        self.lib = _lib.load()
+        self.lib.mmr_decode_tsv.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]
+        n, R, F = int(max_records), int(max_boxes), int(feat_dim)
+        self.cap, self.R, self.F, self.n_threads = n, R, F, n_threads
+        self.buf = {"product_id": _host((n,), torch.int64, pin), "image_h": _host((n,), torch.int32, pin),
+                    "image_w": _host((n,), torch.int32, pin), "num_boxes": _host((n,), torch.int32, pin),
+                    "boxes4": _host((n, R, 4), torch.float32, pin), "feats": _host((n, R, F), torch.float32, pin),
+                    "class_labels": _host((n, R), torch.int64, pin), "query_id": _host((n,), torch.int64, pin)}
+        self.qoff = torch.empty((n, 2), dtype=torch.int64)
+        self.qcap = n * max_query_bytes
+        self.qtext = C.create_string_buffer(self.qcap)
+        self.desc = _DecodeOut(R, F, *[self.buf[k].data_ptr() for k in ("product_id", "image_h", "image_w", "num_boxes",
+                                                                        "boxes4", "feats", "class_labels", "query_id")],
+                               self.qoff.data_ptr(), C.cast(self.qtext, C.c_void_p), self.qcap)
+
+    def decode(self, lines: Sequence[bytes]) -> Dict[str, object]:
+        """Returns views of the first len(lines) records of the internal arrays (valid until the next decode)."""
+        n = len(lines)
+        if n > self.cap:
+            raise ValueError(f"{n} lines exceed the decoder capacity {self.cap}")
+        out: Dict[str, object] = {k: v[:n] for k, v in self.buf.items()}
+        if n == 0:
+            out["queries"] = []
+            return out
+        arr = (C.c_char_p * n)(*lines)
+        lens = (C.c_size_t * n)(*map(len, lines))
+        _lib.check(self.lib.mmr_decode_tsv(arr, lens, n, C.byref(self.desc), self.n_threads))
+        raw = self.qtext.raw if n * 64 > self.qcap else None
+        if raw is None:
+            out["queries"] = [C.string_at(C.addressof(self.qtext) + o, l).decode("utf-8") for o, l in self.qoff[:n].tolist()]
+        else:
+            out["queries"] = [raw[o:o + l].decode("utf-8") for o, l in self.qoff[:n].tolist()]
+        return out
+
+
+def decode_lines(lines: Sequence[bytes], max_boxes: int = 10, feat_dim: int = 2048, n_threads: int = 0,
+                 pin: bool = True) -> Dict[str, object]:
+    """One-shot convenience over RecordDecoder.  Returns product_id [n] i64, image_h / image_w / num_boxes [n] i32,
+    boxes4 [n,R,4] f32 (raw pixels), feats [n,R,F] f32, class_labels [n,R] i64, query_id [n] i64, queries (list of str)."""
+    longest_query_bound = 1024
+    while True:
+        dec = RecordDecoder(max(len(lines), 1), max_boxes, feat_dim, n_threads, pin, max_query_bytes=longest_query_bound)
+        try:
+            return dec.decode(lines)
+        except _lib.MmrError as e:
+            if "query text buffer too small" not in str(e) or longest_query_bound > (1 << 24):
+                raise
+            longest_query_bound *= 16
+
+
+def load_label_map(path: str) -> Dict[int, str]:
+    """multimodal_labels.txt -> {class id: phrase}, punctuation replaced as at load_data_v4.py:34-38."""
+    m = {}
+    with open(path, encoding="utf-8") as f:
+        for line in f:
+            arr = line.strip().split("\t")
+            if len(arr) < 2:
+                continue
+            label = arr[1].replace(",", " ").replace(".", " ").replace("(", " ").replace(")", " ")
+            m[int(arr[0])] = label.strip()
+    return m
+
+
+def _pad(ids: List[int], n: int) -> List[int]:
+    return (ids + [0] * n)[:n]      # seq_padding: zero pad / truncate
+
+
+class FeedAssembler:
+    """Tokenises queries and class-label phrases (both cached: ~33 phrases, <= 1 k distinct queries per test set) and
+    builds the scorer feeds of one decoded batch."""
+
+    def __init__(self, cfg: ModelConfig, tokenizer, label_map: Dict[int, str]):
+        self.cfg, self.tok = cfg, tokenizer
+        self._q: Dict[str, List[int]] = {}
+        top = max(label_map) + 1 if label_map else 1
+        self.label_table = np.zeros((top, cfg.label_len), np.int32)      # class id -> padded token ids
+        for cid, phrase in label_map.items():
+            self.label_table[cid] = _pad(tokenizer.convert_tokens_to_ids(tokenizer.tokenize(phrase)), cfg.label_len)
+
+    def query_ids(self, query: str) -> List[int]:
+        ids = self._q.get(query)
+        if ids is None:
+            ids = self.tok.convert_tokens_to_ids(["[CLS]"] + self.tok.tokenize(query) + ["[SEP]"])
+            self._q[query] = ids
+        return ids
+
+    def assemble(self, batch: Dict[str, object], device: Optional[torch.device] = None) -> Dict[str, torch.Tensor]:
+        cfg = self.cfg
+        n, R, Lq = len(batch["queries"]), cfg.nbox, cfg.lq
+        q = np.zeros((n, Lq), np.int32)
+        qlen = np.zeros(n, np.int32)
+        for i, s in enumerate(batch["queries"]):
+            ids = self.query_ids(s)
+            qlen[i] = min(len(ids), Lq)             # len(idx_query) before padding (load_data_v4.py:259), capped
+            q[i] = _pad(ids, Lq)
+        nb = np.minimum(batch["num_boxes"].numpy(), R).astype(np.int32)
+        valid = np.arange(R)[None, :] < nb[:, None]
+        cls = batch["class_labels"].numpy()
+        label_ids = self.label_table[np.clip(cls, 0, len(self.label_table) - 1)] * valid[..., None]
+        feeds = {"query_ids": torch.from_numpy(q), "label_ids": torch.from_numpy(label_ids.astype(np.int32)),
+                 "feats": batch["feats"]}
+        if cfg.kind == ZK:
+            feeds.update(segment_ids=torch.from_numpy(np.tile(np.array([0] * Lq + [1] * R, np.int32), (n, 1))),
+                         len_query=torch.from_numpy(qlen), num_boxes=torch.from_numpy(nb),
+                         labels=torch.ones(n, dtype=torch.int32))               # load_data_v4.py:204, 264-265
+        elif cfg.kind == LDS:
+            feeds.update(segment_ids=torch.zeros((n, Lq), dtype=torch.int32))   # load_data_pred.py:159
+        else:
+            feeds.update(query_mask=torch.from_numpy((np.arange(Lq)[None, :] < qlen[:, None]).astype(np.int32)),
+                         visn_mask=torch.from_numpy(valid.astype(np.int32)))
+        if cfg.kind != LDS:
+            feeds["boxes"] = normalize_boxes(batch["boxes4"], batch["image_h"], batch["image_w"],
+                                             with_area=cfg.kind == ZK, device=device)
+        return feeds
+
+
+def normalize_boxes(boxes4: torch.Tensor, image_h: torch.Tensor, image_w: torch.Tensor, with_area: bool,
+                    device: Optional[torch.device] = None) -> torch.Tensor:
+    """[n,R,4] raw boxes -> [n,R,5] (zk) or [n,R,4] (lxmert) on the GPU (mmr_boxes_normalize)."""
+    lib = _lib.load()
+    dev = device or torch.device("cuda", torch.cuda.current_device())
+    b = boxes4.to(dev, non_blocking=True).contiguous()
+    h = image_h.to(dev, non_blocking=True).to(torch.int32).contiguous()
+    w = image_w.to(dev, non_blocking=True).to(torch.int32).contiguous()
+    n, R = b.shape[0], b.shape[1]
+    out = torch.empty((n, R, 5 if with_area else 4), dtype=torch.float32, device=dev)
+    lib.mmr_boxes_normalize.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
+                                        C.c_void_p]
+    _lib.check(lib.mmr_boxes_normalize(b.data_ptr(), h.data_ptr(), w.data_ptr(), n, R, int(with_area), out.data_ptr(),
+                                       torch.cuda.current_stream(dev).cuda_stream))
+    return out

@@ -1,0 +1,164 @@
+"""CPU tests of the rows SURVEY.md section 8f marks "next": record decode (N1, host C++ through the C ABI -- no GPU
+involved), WordPiece tokenisation (N2, pinned by the reference's own tokenizer classes) and checkpoint name mapping (N3)."""
+import base64
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from kddcup_2020_multimodalitiesrecall_2nd_place_b200 import checkpoints, records, synth, tokenizer
+from kddcup_2020_multimodalitiesrecall_2nd_place_b200.config import LXMERT, ZK, ModelConfig
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+# ------------------------------------------------------------------------------------------------ N2 tokenizer
+def _kat():
+    with open(os.path.join(GOLD, "tokenizer_kat.json"), encoding="utf-8") as f:
+        return json.load(f)
+
+
+def test_tokenizer_matches_reference_classes_on_golden():
+    """tests/golden/tokenizer_kat.json = outputs of imagebert_zk/tokenization.py (FullTokenizer) and
+    lxmert/src/lxrt/tokenization.py (BertTokenizer) themselves (tools/make_golden.py --tokenizer)."""
+    k = _kat()
+    vocab = {t: i for i, t in enumerate(k["vocab"])}
+    tf_tok = tokenizer.FullTokenizer(vocab=vocab, do_lower_case=True)                                  # 200-char limit
+    lx_tok = tokenizer.FullTokenizer(vocab=vocab, do_lower_case=True, max_input_chars_per_word=100)    # lxmert's
+    assert len(k["cases"]) >= 15
+    for c in k["cases"]:
+        a = tf_tok.tokenize(c["text"])
+        assert a == c["tf_tokens"], c["text"]
+        assert tf_tok.convert_tokens_to_ids(a) == c["tf_ids"]
+        b = lx_tok.tokenize(c["text"])
+        assert b == c["lxmert_tokens"], c["text"]
+        assert lx_tok.convert_tokens_to_ids(b) == c["lxmert_ids"]
+    assert tf_tok.convert_ids_to_tokens(k["cases"][0]["tf_ids"]) == k["cases"][0]["tf_tokens"]
+    with pytest.raises(KeyError):
+        tf_tok.convert_tokens_to_ids(["not-in-vocab"])
+
+
+def test_mirror_module_exposes_reference_names():
+    from kddcup_2020_multimodalitiesrecall_2nd_place_b200.code.imagebert_zk import tokenization
+    assert tokenization.whitespace_tokenize("  a  b ") == ["a", "b"] and tokenization.whitespace_tokenize("") == []
+    assert {"FullTokenizer", "BasicTokenizer", "WordpieceTokenizer", "load_vocab"} <= set(dir(tokenization))
+
+
+# ------------------------------------------------------------------------------------------------ N1 decode
+def _make_lines(n, rng, max_nb=14, bad=None):
+    lines, want = [], []
+    for i in range(n):
+        nb = int(rng.integers(1, max_nb + 1))
+        h, w = int(rng.integers(200, 900)), int(rng.integers(200, 900))
+        boxes = (rng.random((nb, 4)) * 500).astype(np.float32)
+        feats = rng.standard_normal((nb, 2048)).astype(np.float32)
+        labels = rng.integers(0, 33, nb).astype(np.int64)
+        query = ["women's leather shoes", "forest style 连衣裙", "kids wash basin"][i % 3] + f" {i}"
+        fields = [str(1000 + i), str(h), str(w), str(nb), base64.b64encode(boxes.tobytes()).decode(),
+                  base64.b64encode(feats.tobytes()).decode(), base64.b64encode(labels.tobytes()).decode(), query, str(7 * i)]
+        lines.append(("\t".join(fields) + "\n").encode("utf-8"))
+        want.append((1000 + i, h, w, nb, boxes, feats, labels, query, 7 * i))
+    return lines, want
+
+
+def _reference_read_line(line):
+    """The decode part of read_line (imagebert_zk/load_data_v4.py:133-147), verbatim semantics."""
+    arr = line.decode("utf-8").strip().split("\t")
+    nb = int(arr[3])
+    boxes = np.frombuffer(base64.b64decode(arr[4]), dtype=np.float32).reshape(nb, 4)
+    feats = np.frombuffer(base64.b64decode(arr[5]), dtype=np.float32).reshape(nb, 2048)
+    labels = np.frombuffer(base64.b64decode(arr[6]), dtype=np.int64).reshape(nb)
+    return int(arr[0]), int(arr[1]), int(arr[2]), nb, boxes, feats, labels, arr[7], int(arr[8])
+
+
+@pytest.mark.parametrize("threads", [1, 4])
+def test_decode_matches_reference_read_line_bit_exact(threads):
+    rng = np.random.default_rng(3)
+    lines, _ = _make_lines(23, rng)
+    R = 10
+    out = records.decode_lines(lines, max_boxes=R, n_threads=threads, pin=False)
+    for i, line in enumerate(lines):
+        pid, h, w, nb, boxes, feats, labels, query, qid = _reference_read_line(line)
+        k = min(nb, R)                                            # seq_padding_2: truncate to the box budget, zero pad
+        assert (out["product_id"][i], out["image_h"][i], out["image_w"][i], out["num_boxes"][i], out["query_id"][i]) \
+            == (pid, h, w, nb, qid)
+        assert out["queries"][i] == query
+        assert np.array_equal(out["boxes4"][i, :k].numpy(), boxes[:k]) and not out["boxes4"][i, k:].any()
+        assert np.array_equal(out["feats"][i, :k].numpy().view(np.uint32), feats[:k].view(np.uint32))
+        assert not out["feats"][i, k:].any()
+        assert np.array_equal(out["class_labels"][i, :k].numpy(), labels[:k]) and not out["class_labels"][i, k:].any()
+
+
+def test_decode_edge_cases_and_errors():
+    from kddcup_2020_multimodalitiesrecall_2nd_place_b200._lib import MmrError
+    assert records.decode_lines([], pin=False)["queries"] == []
+    rng = np.random.default_rng(4)
+    lines, _ = _make_lines(3, rng)
+    cols = lines[1].split(b"\t")
+    with pytest.raises(MmrError, match="line 1: fewer than 9"):
+        records.decode_lines([lines[0], b"\t".join(cols[:6]), lines[2]], pin=False)
+    broken = list(cols)
+    broken[5] = broken[5][:-8]                                   # feature blob too short for num_boxes
+    with pytest.raises(MmrError, match="base64"):
+        records.decode_lines([b"\t".join(broken)], pin=False)
+    broken = list(cols)
+    broken[3] = b"x3"
+    with pytest.raises(MmrError, match="integer"):
+        records.decode_lines([b"\t".join(broken)], pin=False)
+    # CRLF line endings and a missing final newline are accepted (.strip())
+    ok = records.decode_lines([lines[0].rstrip(b"\n") + b"\r\n", lines[2].rstrip(b"\n")], pin=False)
+    assert len(ok["queries"]) == 2
+
+
+def test_feed_assembly_follows_the_loaders():
+    """Token ids / lengths / masks / label phrases as load_data_v4.py:148-163, 204, 259-265 and utils.py:38-59 build them."""
+    k = _kat()
+    vocab = {t: i for i, t in enumerate(k["vocab"])}
+    tok = tokenizer.FullTokenizer(vocab=vocab)
+    label_map = {0: "women dress", 1: "leather shoes", 2: "kids", 5: "wash basin"}
+    cfg = ModelConfig(LXMERT, n_layers=1, n_r_layers=1, n_x_layers=1, lq=12, nbox=4, vocab=len(vocab))
+    fa = records.FeedAssembler(cfg, tok, label_map)
+    batch = {"queries": ["women leather shoes", "kids"], "num_boxes": torch.tensor([2, 6], dtype=torch.int32),
+             "class_labels": torch.tensor([[1, 5, 0, 0], [2, 0, 1, 5]]), "feats": torch.zeros(2, 4, 2048)}
+    cfg_lds = ModelConfig("imagebert_lds", n_layers=1, lq=12, nbox=4, vocab=len(vocab))
+    feeds = records.FeedAssembler(cfg_lds, tok, label_map).assemble(batch)
+    ids = lambda s: tok.convert_tokens_to_ids(tok.tokenize(s))
+    want_q0 = [vocab["[CLS]"]] + ids("women leather shoes") + [vocab["[SEP]"]]
+    assert feeds["query_ids"][0, :len(want_q0)].tolist() == want_q0 and not feeds["query_ids"][0, len(want_q0):].any()
+    assert feeds["label_ids"][0, 0, :2].tolist() == ids("leather shoes") and not feeds["label_ids"][0, 2:].any()
+    assert feeds["label_ids"][1, 3, :2].tolist() == ids("wash basin")          # 6 boxes in the file, 4 slots kept
+    assert feeds["segment_ids"].shape == (2, 12) and not feeds["segment_ids"].any()
+    assert fa.label_table.shape == (6, 8)
+
+
+# ------------------------------------------------------------------------------------------------ N3 checkpoints
+def test_tf_checkpoint_selection_prefers_ema_and_drops_optimizer_slots(tmp_path):
+    cfg = ModelConfig(ZK, n_layers=1, lq=20, nbox=10, vocab=50)
+    w = synth.make_weights(cfg, seed=1)
+    entries = {}
+    for k_, v in w.items():
+        entries[k_] = v + 1.0                                    # raw variable (must lose against its shadow)
+        entries[k_ + "/ExponentialMovingAverage"] = v
+        entries[k_ + "/adam_m"] = np.zeros_like(v)
+        entries[k_ + "/adam_v"] = np.zeros_like(v)
+    entries["global_step"] = np.array(1234, np.int64)
+    got, src = checkpoints.select_tf_variables(entries, prefer_ema=True, wanted=w.keys())
+    assert set(got) == set(w) and all(np.array_equal(got[k_], w[k_]) for k_ in w)
+    assert all(s.endswith("/ExponentialMovingAverage") for s in src.values())
+    raw, _ = checkpoints.select_tf_variables(entries, prefer_ema=False)
+    assert np.array_equal(raw["bert/pooler/dense/bias"], w["bert/pooler/dense/bias"] + 1.0) and "global_step" not in raw
+    np.savez(tmp_path / "ckpt.npz", **{k_.replace("/", "|"): v for k_, v in list(entries.items())[:3]})
+    with pytest.raises(KeyError, match="checkpoint lacks"):
+        checkpoints.select_tf_variables({"a": np.zeros(1)}, wanted=["b"])
+
+
+def test_pth_import_strips_dataparallel_prefix(tmp_path):
+    cfg = ModelConfig(LXMERT, n_layers=1, n_r_layers=1, n_x_layers=1, vocab=40)
+    w = synth.make_weights(cfg, seed=2)
+    sd = {"module." + k_: torch.from_numpy(v).double() for k_, v in w.items()}
+    sd["module.some.counter"] = torch.tensor(3)
+    torch.save(sd, tmp_path / "BEST.pth")
+    got = checkpoints.load_pth(str(tmp_path / "BEST"))           # the reference passes the path without ".pth"
+    assert set(got) == set(w) and all(got[k_].dtype == np.float32 and np.array_equal(got[k_], w[k_]) for k_ in w)

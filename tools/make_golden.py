@@ -94,8 +94,58 @@ def lxmert_ref():
         print("lxmert_ref", tag, out["probs"][:, 1].numpy())
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--tokenizer" not in sys.argv:
     os.makedirs(OUT, exist_ok=True)
     ensemble_kat()
     ndcg_kat()
     lxmert_ref()
+
+
+# ---------------------------------------------------------------------------------------------- tokenizer KAT
+def make_tokenizer_golden(out_path=os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests",
+                                                "golden", "tokenizer_kat.json")):
+    """Runs the reference's OWN tokenizer classes (imagebert_zk/tokenization.py with `tensorflow` stubbed: it only uses
+    tf.gfile to read the vocab; lxmert/src/lxrt/tokenization.py as is) on a synthetic vocabulary and a set of strings,
+    and stores vocabulary, strings, tokens and ids."""
+    import importlib
+    import importlib.util
+    import json
+    import tempfile
+    import types
+    specials = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"]
+    singles = list("abcdefghijklmnopqrstuvwxyz0123456789") + list("!\"#$%&'()*+,-./:;<=>?@[\\]^_`{|}~") + ["α", "β", "é"]
+    pieces = ["sen", "department", "of", "forest", "style", "women", "men", "leather", "shoes", "shoe", "wash", "basin",
+              "run", "##ning", "##ing", "##s", "##ed", "un", "##aff", "##able", "t", "shirt", "kids", "cafe", "naive",
+              "hello", "world", "2020", "##20", "20", "3d", "x", "##x", "##xx", "##xxx", "xxxx", "zero", "tab", "sep",
+              "女", "士", "皮", "鞋", "包", "##a", "##b", "##c", "the", "for", "and", "black", "white", "red", "dress"]
+    vocab = specials + singles + pieces
+    texts = ["sen department of Women's leather shoes", "forest style  women dress", "女士皮鞋 black 包", "Running shoes for MEN",
+             "unaffable T-shirt (2020)", "café naïve HELLO wörld", "kids' wash\tbasin red", "​zero emoji\U0001F600 end",
+             "x" * 120, "x" * 250, "α-β ３Ｄ", "###ing ##s", "", "   ", "unknownword qqq", "shoes,shoe.shoes!", "ＡＢＣ abc",
+             "the red-and-white dress for women and men", "20202020 20 2020a"]
+    tf = types.ModuleType("tensorflow")
+    tf.gfile = types.SimpleNamespace(GFile=lambda p, m="r": open(p, m, encoding="utf-8"))
+    sys.modules.setdefault("tensorflow", tf)
+    with tempfile.TemporaryDirectory() as d:
+        vf = os.path.join(d, "vocab.txt")
+        with open(vf, "w", encoding="utf-8") as f:
+            f.write("\n".join(vocab) + "\n")
+        spec = importlib.util.spec_from_file_location("ref_tok_zk", os.path.join(REF, "code/imagebert_zk/tokenization.py"))
+        zk = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(zk)
+        sys.path.insert(0, os.path.join(REF, "code/lxmert/src"))
+        lx = importlib.import_module("lxrt.tokenization")
+        tz = zk.FullTokenizer(vocab_file=vf, do_lower_case=True)
+        tl = lx.BertTokenizer(vf, do_lower_case=True)
+        cases = []
+        for t in texts:
+            a, b = tz.tokenize(t), tl.tokenize(t)
+            cases.append({"text": t, "tf_tokens": a, "tf_ids": tz.convert_tokens_to_ids(a), "lxmert_tokens": b,
+                          "lxmert_ids": tl.convert_tokens_to_ids(b)})
+    with open(out_path, "w", encoding="utf-8") as f:
+        json.dump({"vocab": vocab, "cases": cases}, f, ensure_ascii=False, indent=0)
+    print("wrote", out_path, len(cases), "cases")
+
+
+if __name__ == "__main__" and "--tokenizer" in sys.argv:
+    make_tokenizer_golden()
