@@ -58,9 +58,9 @@ def test_tsv_to_scores_against_oracle(kind):
     queries = ["women's leather shoes", "forest style dress 女士", "kids wash basin red", "running shoes for men"]
     R, Lq, n = 10, 20, 12
     if kind == ZK:
-        cfg = ModelConfig(ZK, n_layers=2, lq=Lq, nbox=R, vocab=len(vocab))
+        cfg = ModelConfig(ZK, n_layers=2, lq=Lq, nbox=R, vocab=len(k["vocab"]))
     else:
-        cfg = ModelConfig(LXMERT, n_layers=2, n_r_layers=1, n_x_layers=1, lq=Lq, nbox=R, vocab=len(vocab))
+        cfg = ModelConfig(LXMERT, n_layers=2, n_r_layers=1, n_x_layers=1, lq=Lq, nbox=R, vocab=len(k["vocab"]))
     lines = _lines(n, 13, np.random.default_rng(5), queries)           # some records exceed the 10-box budget
     batch = records.decode_lines(lines, max_boxes=R)
     feeds = records.FeedAssembler(cfg, tok, label_map).assemble(batch)

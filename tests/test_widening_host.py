@@ -118,11 +118,11 @@ def test_feed_assembly_follows_the_loaders():
     vocab = {t: i for i, t in enumerate(k["vocab"])}
     tok = tokenizer.FullTokenizer(vocab=vocab)
     label_map = {0: "women dress", 1: "leather shoes", 2: "kids", 5: "wash basin"}
-    cfg = ModelConfig(LXMERT, n_layers=1, n_r_layers=1, n_x_layers=1, lq=12, nbox=4, vocab=len(vocab))
+    cfg = ModelConfig(LXMERT, n_layers=1, n_r_layers=1, n_x_layers=1, lq=12, nbox=4, vocab=len(k["vocab"]))
     fa = records.FeedAssembler(cfg, tok, label_map)
     batch = {"queries": ["women leather shoes", "kids"], "num_boxes": torch.tensor([2, 6], dtype=torch.int32),
              "class_labels": torch.tensor([[1, 5, 0, 0], [2, 0, 1, 5]]), "feats": torch.zeros(2, 4, 2048)}
-    cfg_lds = ModelConfig("imagebert_lds", n_layers=1, lq=12, nbox=4, vocab=len(vocab))
+    cfg_lds = ModelConfig("imagebert_lds", n_layers=1, lq=12, nbox=4, vocab=len(k["vocab"]))
     feeds = records.FeedAssembler(cfg_lds, tok, label_map).assemble(batch)
     ids = lambda s: tok.convert_tokens_to_ids(tok.tokenize(s))
     want_q0 = [vocab["[CLS]"]] + ids("women leather shoes") + [vocab["[SEP]"]]
