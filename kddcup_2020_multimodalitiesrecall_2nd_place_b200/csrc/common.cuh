@@ -97,7 +97,7 @@ __device__ __forceinline__ float warp_max(float v) {
 // Activations of the hot path (fp32 in registers).
 __device__ __forceinline__ float gelu_tanh_f(float x) {
   // pixelbert.py:326-328: 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))
-  const float u = 0.7978845608028654f * x * fmaf(0.044715f * x, x, 1.0f);
+  const float u = x * fmaf(x * x, 0.7978845608028654f * 0.044715f, 0.7978845608028654f);   // 3 FP ops instead of 4
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
   const float hx = 0.5f * x;
