@@ -216,11 +216,16 @@ def main():
     e0.record()
     for k in range(K):
         sc.forward_device(dev_sets[k % n_sets], probs_out=scores[k])
+    e_fw = torch.cuda.Event(enable_timing=True)
+    e_fw.record()
     if world > 1:
         dist.all_gather_into_tensor(gathered.view(-1), scores[:, :, 1].contiguous().view(-1))
     e1.record()
     barrier()
     clocks = sampler.stop() if sampler else None
+    if os.environ.get("MMR_BENCH_DEBUG"):
+        print(f"DEBUG rank {rank}: forwards {e0.elapsed_time(e_fw):.2f} ms, gather {e_fw.elapsed_time(e1):.2f} ms",
+              file=sys.stderr, flush=True)
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)

@@ -236,21 +236,30 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           st_volatile_u32x2(mine, __float_as_uint(mean_i), tag);
           st_volatile_u32x2(mine + 8, __float_as_uint(m2_i), tag);
         }
+        // all 12 words are requested together on every probe: the wait costs one L2 round trip after the last
+        // partner's publish, not one per entry
         float means[kLnSlots], m2_tot = 0.f;
         mean = 0.f;
+        uint2 a[kLnSlots], b[kLnSlots];
+        uint32_t spins = 0;
+        for (;;) {
+          bool all_in = true;
+#pragma unroll
+          for (int s = 0; s < kLnSlots; ++s) {
+            const uint8_t* e = reinterpret_cast<const uint8_t*>(tab + size_t(s) * kPairRows);
+            a[s] = ld_volatile_u32x2(e);
+            b[s] = ld_volatile_u32x2(e + 8);
+          }
+#pragma unroll
+          for (int s = 0; s < kLnSlots; ++s) all_in = all_in && a[s].y == tag && b[s].y == tag;
+          if (all_in) break;
+          if (++spins > MMR_SPIN_LIMIT) __trap();
+        }
 #pragma unroll
         for (int s = 0; s < kLnSlots; ++s) {
-          const uint8_t* e = reinterpret_cast<const uint8_t*>(tab + size_t(s) * kPairRows);
-          uint2 a = ld_volatile_u32x2(e), b = ld_volatile_u32x2(e + 8);
-          uint32_t spins = 0;
-          while (a.y != tag || b.y != tag) {
-            if (++spins > MMR_SPIN_LIMIT) __trap();
-            a = ld_volatile_u32x2(e);
-            b = ld_volatile_u32x2(e + 8);
-          }
-          means[s] = __uint_as_float(a.x);
+          means[s] = __uint_as_float(a[s].x);
           mean += means[s];
-          m2_tot += __uint_as_float(b.x);
+          m2_tot += __uint_as_float(b[s].x);
         }
         mean *= (1.0f / kLnSlots);
 #pragma unroll

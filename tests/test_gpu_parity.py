@@ -213,3 +213,50 @@ def test_error_behaviour():
     bad["featureemb/fully_connected/biases"] = np.zeros(5, np.float32)
     with pytest.raises(MmrError, match="featureemb/fully_connected/biases"):
         _scorer(cfg, bad, 4)
+
+
+def test_cfg5_three_model_ensemble_topk_against_oracle():
+    """BASELINE configs[4] at test size: the same candidate pairs scored by imagebert_zk (twice: the reference feeds the
+    plain and the sen2forest-rewritten query file through the same model), imagebert_lds and lxmert, merged by the
+    main.py ensemble; merged scores within the tolerance of the oracle's, and identical top-5 lists wherever the oracle
+    separates neighbours by more than the tolerance allows to swap."""
+    from kddcup_2020_multimodalitiesrecall_2nd_place_b200 import ensemble
+    from oracle import ensemble as oracle_ensemble
+    nq, per_q = 6, 8
+    B = nq * per_q
+    shapes = dict(lq=20, nbox=10, vocab=2000)
+    cfgs = {ZK: ModelConfig(ZK, n_layers=2, **shapes), LDS: ModelConfig(LDS, n_layers=2, **shapes),
+            LXMERT: ModelConfig(LXMERT, n_layers=2, n_r_layers=1, n_x_layers=1, **shapes)}
+    got, ref = {}, {}
+    for kind, cfg in cfgs.items():
+        w = synth.make_weights(cfg, seed=synth.SEED0 + 5, trained_like=True)   # spread-out scores
+        inp = synth.make_inputs(cfg, B, seed=synth.SEED0 + 5, n_queries=nq)
+        sc = _scorer(cfg, w, B)
+        got[kind] = _gpu_probs(sc, inp)[0][:, 1].numpy().astype(np.float64)
+        ref[kind] = _oracle(cfg, w, inp)["probs"][:, 1].numpy().astype(np.float64)
+        sc.close()
+    qids = [f"q{i // per_q}" for i in range(B)]
+    pids = [f"p{i}" for i in range(B)]                       # every pair its own product: the uniqueness filter passes
+
+    def merged(scores):
+        d = {k: ensemble.scores_from_arrays(qids, pids, v) for k, v in scores.items()}
+        return ensemble.merge_and_select(d[ZK], d[ZK], d[LDS], d[LXMERT])
+
+    rows_g, merged_g = merged(got)
+    o = {k: oracle_ensemble.merge_and_select.__globals__["OrderedDict"]() for k in ref}
+    for k, v in ref.items():
+        for q, p_, s in zip(qids, pids, v):
+            o[k].setdefault(q, {})[p_] = float(s)
+    rows_o, merged_o = oracle_ensemble.merge_and_select(o[ZK], {q: dict(r) for q, r in o[ZK].items()}, o[LDS], o[LXMERT])
+    tol = TOL_STRESS                                          # trained-like weights (see the header of this file)
+    assert merged_g.shape == (B,)                             # flat, in the (query, candidate) order of the inputs
+    for i, (q, p_) in enumerate(zip(qids, pids)):
+        assert abs(merged_g[i] - merged_o[q][p_]) <= tol
+    top_o, top_g = dict(rows_o), dict(rows_g)
+    assert set(top_o) == set(top_g) and len(top_o) == nq
+    for q in top_o:
+        s = sorted(merged_o[q].values(), reverse=True)
+        if min(a - b for a, b in zip(s[:6], s[1:7])) > 2 * tol:      # unambiguous at the stated tolerance
+            assert top_g[q] == top_o[q], q
+        else:
+            assert len(set(top_g[q]) & set(top_o[q])) >= 4
