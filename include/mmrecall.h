@@ -103,6 +103,25 @@ mmr_status mmr_boxes_normalize(const float* boxes4, const int32_t* image_h, cons
                                int max_boxes, int with_area, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Ensemble on the device: code/main.py:41-104 (weighted merge, product-uniqueness filter, per-query
+ * top-k with the < k fall-back) and imagebert_lds/src/evaluation.py:4-38 (nDCG@k).  All pointers are device pointers.
+ * Pairs are flattened in the reference's iteration order with the pairs of a query contiguous
+ * (query_start [n_queries + 1]); scores missing from a file are back-filled by the caller (main.py:50-58) before
+ * upload.  weights4 is a HOST array of 4 doubles.  merged [n_pairs] fp64 (bit-identical to the host ensemble);
+ * top [n_queries, topk] pair indices (-1: none); status [n_queries]: 0 = query not written (no survivor),
+ * 1 = filtered top-k, 2 = fall-back top-k (written after the status-1 queries, main.py:101-104).
+ * workspace: >= 20 * n_products bytes.
+ * ---------------------------------------------------------------------------------------------- */
+mmr_status mmr_ensemble_topk(const double* s1, const double* s2, const double* s3, const double* s4,
+                             const int32_t* product_of, const int32_t* query_start, int64_t n_pairs, int32_t n_queries,
+                             int32_t n_products, const double* weights4, double margin, double tie, int32_t topk,
+                             double* merged, int32_t* top, int32_t* status, void* workspace, size_t workspace_bytes,
+                             void* stream);
+/* gt / gt_start: ground-truth product indices per query (CSR); ndcg [n_queries], -1 for queries without a prediction. */
+mmr_status mmr_ndcg_at_k(const int32_t* top, const int32_t* product_of, const int32_t* gt, const int32_t* gt_start,
+                         int32_t n_queries, int32_t topk, double* ndcg, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Operator level (one kernel each).  Used by the model driver below and by the parity tests.
  * ---------------------------------------------------------------------------------------------- */
 

@@ -16,7 +16,7 @@ TUNE_GEMM_PAIR, TUNE_GEMM_P16, TUNE_GEMM_TAIL, TUNE_GEMM_CLUSTER, TUNE_GEMM_LN, 
 # every symbol include/mmrecall.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "mmr_last_error", "mmr_abi_version", "mmr_device_check", "mmr_set_tuning",
-    "mmr_gemm", "mmr_gemm_layernorm", "mmr_gemm_layernorm_supported", "mmr_layernorm", "mmr_attention", "mmr_cast16", "mmr_am_softmax_head", "mmr_linear_head", "mmr_decode_tsv", "mmr_boxes_normalize",
+    "mmr_gemm", "mmr_gemm_layernorm", "mmr_gemm_layernorm_supported", "mmr_layernorm", "mmr_attention", "mmr_cast16", "mmr_am_softmax_head", "mmr_linear_head", "mmr_decode_tsv", "mmr_boxes_normalize", "mmr_ensemble_topk", "mmr_ndcg_at_k",
     "mmr_create", "mmr_destroy", "mmr_forward", "mmr_set_debug_taps", "mmr_get_activation",
     "mmr_launches_per_forward", "mmr_set_profiling", "mmr_get_profile",
 ]

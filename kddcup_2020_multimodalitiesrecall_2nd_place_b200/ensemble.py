@@ -119,6 +119,49 @@ def merge_and_select(d1: ScoreDict, d2: ScoreDict, d3: ScoreDict, d4: ScoreDict,
     return rows, merged
 
 
+def merge_and_select_gpu(d1: ScoreDict, d2: ScoreDict, d3: ScoreDict, d4: ScoreDict,
+                         weights: Sequence[float] = WEIGHTS, margin: float = MARGIN, tie: float = TIE,
+                         topk: int = TOPK, device: int = 0) -> Tuple[List[Tuple[str, List[str]]], np.ndarray]:
+    """Same result as merge_and_select, computed by the device kernels of csrc/ensemble.cu (mmr_ensemble_topk):
+    flattening / back-filling of the score files stays on the host (dictionary work), merge + uniqueness filter + top-k
+    run on the GPU.  Raises without an sm_100 device (no CPU fallback behind this name)."""
+    import ctypes as C
+
+    import torch
+
+    from . import _lib
+    lib = _lib.load()
+    q_names, p_names, qi, pi, S = _flatten(d1, d2, d3, d4)
+    n = int(qi.shape[0])
+    if n == 0:
+        return [], np.zeros(0)
+    dev = torch.device("cuda", device)
+    q_starts = np.nonzero(np.r_[True, qi[1:] != qi[:-1]])[0]
+    query_start = torch.from_numpy(np.r_[q_starts, n].astype(np.int32)).to(dev)
+    nq, P = len(q_starts), len(p_names)
+    s = [torch.from_numpy(np.ascontiguousarray(S[k], dtype=np.float64)).to(dev) for k in range(4)]
+    product_of = torch.from_numpy(pi.astype(np.int32)).to(dev)
+    merged = torch.empty(n, dtype=torch.float64, device=dev)
+    top = torch.empty((nq, topk), dtype=torch.int32, device=dev)
+    status = torch.empty(nq, dtype=torch.int32, device=dev)
+    ws = torch.empty(20 * P, dtype=torch.uint8, device=dev)
+    w = (C.c_double * 4)(*[float(x) for x in weights])
+    lib.mmr_ensemble_topk.argtypes = [C.c_void_p] * 6 + [C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_double,
+                                                        C.c_double, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                        C.c_void_p, C.c_size_t, C.c_void_p]
+    _lib.check(lib.mmr_ensemble_topk(s[0].data_ptr(), s[1].data_ptr(), s[2].data_ptr(), s[3].data_ptr(),
+                                     product_of.data_ptr(), query_start.data_ptr(), n, nq, P, w, float(margin),
+                                     float(tie), int(topk), merged.data_ptr(), top.data_ptr(), status.data_ptr(),
+                                     ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
+    top_h, status_h = top.cpu().numpy(), status.cpu().numpy()
+    rows: List[Tuple[str, List[str]]] = []
+    for want in (1, 2):                                         # filtered queries first, then the fall-backs
+        for k, a in enumerate(q_starts):
+            if status_h[k] == want:
+                rows.append((q_names[qi[a]], [p_names[pi[i]] for i in top_h[k] if i >= 0]))
+    return rows, merged.cpu().numpy()
+
+
 def write_submission(path: str, rows: List[Tuple[str, List[str]]]) -> None:
     """main.py:88-90, 99, 104."""
     with open(path, "w", newline="") as f:
