@@ -61,15 +61,27 @@ int mmr_abi_version(void);
  *   MMR_TUNE_GEMM_TAIL     (env MMR_GEMM_TAIL,    default 1) split the last partial wave of that GEMM along N
  *   MMR_TUNE_GEMM_CLUSTER  (env MMR_GEMM_CLUSTER, default 1) 1 = lone CTA pairs, 2 = 4-CTA clusters sharing W by
  *                                                            TMA multicast (measured slower: 132 of 148 SMs)
- *   MMR_TUNE_GEMM_LN       (env MMR_GEMM_LN,      default 1) fused projection + residual + LayerNorm kernel
+ *   MMR_TUNE_GEMM_LN       (env MMR_GEMM_LN,      default 1) fused projection + residual + LayerNorm kernel: 1 = three
+ *                                                            CTA pairs per 256-row block meeting through a global table
+ *                                                            (gemm_ln_sm100.cu), 2 = one pair owns the block and all 768
+ *                                                            columns (gemm_lnrow_sm100.cu), 0 = GEMM + LayerNorm kernels
  *   MMR_TUNE_PDL           (env MMR_PDL,          default 1) programmatic dependent launch between the kernels
  *   MMR_TUNE_ATTN_TMA      (env MMR_ATTN_TMA,     default 0) persistent TMA-pipelined mma.sync attention kernel
  *                                                            (measured slower than one CTA per (pair, head): 40 vs 32 us)
- *   MMR_TUNE_ATTN_TC       (env MMR_ATTN_TC,      default 0) tcgen05 / TMEM attention kernel (attention_tc.cu): correct,
- *                                                            40.9 us vs 32.5 us at B=256, S=68 (one item in flight per CTA) */
+ *   MMR_TUNE_ATTN_TC       (env MMR_ATTN_TC,      default 2) tcgen05 / TMEM attention: 2 = pipelined four items deep per
+ *                                                            SM with P kept in TMEM (attention_tc2.cu: 25.5 us at B=256,
+ *                                                            S=68 against 31.7 us for the mma.sync kernel), 1 = first
+ *                                                            version, one item in flight per CTA (attention_tc.cu, 40 us),
+ *                                                            0 = mma.sync kernels
+ *   MMR_TUNE_LN_ROW_CFG    (env MMR_LN_ROW_CFG,   default 0) shared-memory split of the row-owner GEMM+LN kernel as
+ *                                                            three digits (operand stages, fp32 chunk slots, 16-bit
+ *                                                            stages per epilogue warp): 421, 331, 511, 412, 322; 0 = default */
 enum { MMR_TUNE_GEMM_PAIR = 0, MMR_TUNE_GEMM_P16 = 1, MMR_TUNE_GEMM_TAIL = 2, MMR_TUNE_GEMM_CLUSTER = 3,
-       MMR_TUNE_GEMM_LN = 4, MMR_TUNE_PDL = 5, MMR_TUNE_ATTN_TMA = 6, MMR_TUNE_ATTN_TC = 7, MMR_TUNE_COUNT = 8 };
+       MMR_TUNE_GEMM_LN = 4, MMR_TUNE_PDL = 5, MMR_TUNE_ATTN_TMA = 6, MMR_TUNE_ATTN_TC = 7, MMR_TUNE_LN_ROW_CFG = 8,
+       MMR_TUNE_COUNT = 9 };
 mmr_status mmr_set_tuning(int knob, int value);
+/* Current value of a knob (-1 for an unknown one). */
+int mmr_get_tuning(int knob);
 /* MMR_OK iff `device` is an sm_100 part. */
 mmr_status mmr_device_check(int device);
 

@@ -11,11 +11,11 @@ MMR_OK = 0
 DT_FP16, DT_BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_GELU_TANH, ACT_GELU_ERF, ACT_TANH = range(5)
 MODEL_ZK, MODEL_LDS, MODEL_LXMERT = range(3)
-TUNE_GEMM_PAIR, TUNE_GEMM_P16, TUNE_GEMM_TAIL, TUNE_GEMM_CLUSTER, TUNE_GEMM_LN, TUNE_PDL, TUNE_ATTN_TMA, TUNE_ATTN_TC = range(8)
+TUNE_GEMM_PAIR, TUNE_GEMM_P16, TUNE_GEMM_TAIL, TUNE_GEMM_CLUSTER, TUNE_GEMM_LN, TUNE_PDL, TUNE_ATTN_TMA, TUNE_ATTN_TC, TUNE_LN_ROW_CFG = range(9)
 
 # every symbol include/mmrecall.h declares (tests check the .so exports all of them)
 EXPORTS = [
-    "mmr_last_error", "mmr_abi_version", "mmr_device_check", "mmr_set_tuning",
+    "mmr_last_error", "mmr_abi_version", "mmr_device_check", "mmr_set_tuning", "mmr_get_tuning",
     "mmr_gemm", "mmr_gemm_layernorm", "mmr_gemm_layernorm_supported", "mmr_layernorm", "mmr_attention", "mmr_cast16", "mmr_am_softmax_head", "mmr_linear_head", "mmr_decode_tsv", "mmr_boxes_normalize", "mmr_ensemble_topk", "mmr_ndcg_at_k",
     "mmr_create", "mmr_destroy", "mmr_forward", "mmr_set_debug_taps", "mmr_get_activation",
     "mmr_launches_per_forward", "mmr_set_profiling", "mmr_get_profile",
@@ -70,6 +70,8 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.mmr_gemm_layernorm.argtypes = [vp, i64, vp, i64, i32, i32, vp, vp, i64, vp, vp, f32, vp, i64, vp, i64, i32, vp]
     lib.mmr_gemm_layernorm_supported.argtypes = [i32, i32, i32]
     lib.mmr_set_tuning.argtypes = [i32, i32]
+    lib.mmr_get_tuning.argtypes = [i32]
+    lib.mmr_get_tuning.restype = i32
     lib.mmr_am_softmax_head.argtypes = [vp, vp, vp, i32, vp, vp, vp]
     lib.mmr_linear_head.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, vp, vp]
     if True:

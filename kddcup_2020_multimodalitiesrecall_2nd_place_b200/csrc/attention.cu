@@ -470,6 +470,8 @@ mmr_status attention(const void* q, int64_t ldq, const void* k, int64_t ldk, con
                   (reinterpret_cast<uintptr_t>(out16) & 3) == 0,
               "mmr_attention: q/k/v must be 16-byte aligned");
   MMR_REQUIRE(dtype == MMR_DT_BF16 || dtype == MMR_DT_FP16, "mmr_attention: bad dtype %d", dtype);
+  if (attention_tc2_eligible(out16, ldo))
+    return attention_tc2(q, ldq, k, ldk, v, ldv, key_mask, out16, ldo, B, Sq, Sk, heads, dtype, stream);
   if (attention_tc_eligible(out16, ldo))
     return attention_tc(q, ldq, k, ldk, v, ldv, key_mask, out16, ldo, B, Sq, Sk, heads, dtype, stream);
   // the TMA kernel needs out16 rows 16-byte aligned (vector stores) on top of the operand alignment checked above

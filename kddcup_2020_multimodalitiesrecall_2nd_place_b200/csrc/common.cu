@@ -23,7 +23,7 @@ static int g_tuning[MMR_TUNE_COUNT];
 static bool g_tuning_init = false;
 static void tuning_init() {
   static const struct { const char* env; int def; } spec[MMR_TUNE_COUNT] = {
-      {"MMR_GEMM_PAIR", 1}, {"MMR_GEMM_P16", 1}, {"MMR_GEMM_TAIL", 1}, {"MMR_GEMM_CLUSTER", 1}, {"MMR_GEMM_LN", 1}, {"MMR_PDL", 1}, {"MMR_ATTN_TMA", 0}, {"MMR_ATTN_TC", 0}};
+      {"MMR_GEMM_PAIR", 1}, {"MMR_GEMM_P16", 1}, {"MMR_GEMM_TAIL", 1}, {"MMR_GEMM_CLUSTER", 1}, {"MMR_GEMM_LN", 1}, {"MMR_PDL", 1}, {"MMR_ATTN_TMA", 0}, {"MMR_ATTN_TC", 2}, {"MMR_LN_ROW_CFG", 0}};
   for (int i = 0; i < MMR_TUNE_COUNT; ++i) {
     const char* e = getenv(spec[i].env);
     g_tuning[i] = e ? atoi(e) : spec[i].def;
@@ -70,6 +70,7 @@ extern "C" mmr_status mmr_set_tuning(int knob, int value) {
   mmr::g_tuning[knob] = value;
   return MMR_OK;
 }
+extern "C" int mmr_get_tuning(int knob) { return (knob >= 0 && knob < MMR_TUNE_COUNT) ? mmr::tuning(knob) : -1; }
 extern "C" mmr_status mmr_device_check(int device) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) {

@@ -440,6 +440,10 @@ mmr_status gemm_ln(const void* A16, int64_t lda, const void* W16, int64_t ldw, i
                 reinterpret_cast<uintptr_t>(out16) | reinterpret_cast<uintptr_t>(out32) | reinterpret_cast<uintptr_t>(bias) |
                 reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0,
               "gemm_ln: pointers must be 16-byte aligned");
+  // row-owner decomposition (gemm_lnrow_sm100.cu): 2 = always, 3 = only for K <= 1024
+  if (tuning(MMR_TUNE_GEMM_LN) == 2 || (tuning(MMR_TUNE_GEMM_LN) == 3 && K <= 1024))
+    return gemm_lnrow(A16, lda, W16, ldw, M, K, bias, residual, ldr, gamma, beta, eps, out16, ldo16, out32, ldo32, dtype,
+                      stream);
   MMR_TRY(gemm_ln_reserve(M));
   int dev = 0;
   MMR_CUDA_OK(cudaGetDevice(&dev));

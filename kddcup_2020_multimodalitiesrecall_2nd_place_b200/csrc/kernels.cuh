@@ -18,6 +18,11 @@ bool attention_tc_eligible(const void* out16, int64_t ldo);
 mmr_status attention_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                         const int32_t* key_mask, void* out16, int64_t ldo, int B, int Sq, int Sk, int heads, int dtype,
                         cudaStream_t stream);
+// tcgen05 / TMEM attention pipelined four items deep per SM, P kept in TMEM (attention_tc2.cu); same contract
+bool attention_tc2_eligible(const void* out16, int64_t ldo);
+mmr_status attention_tc2(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                         const int32_t* key_mask, void* out16, int64_t ldo, int B, int Sq, int Sk, int heads, int dtype,
+                         cudaStream_t stream);
 mmr_status cast16(const float* x, void* out16, int64_t n, int dtype, cudaStream_t stream);
 // out = LN(A . W^T + bias + residual) for N = 768 in one kernel (gemm_ln_sm100.cu); residual may alias out32.
 bool gemm_ln_eligible(int M, int N, int K, int dtype);
@@ -25,6 +30,11 @@ mmr_status gemm_ln_reserve(int M);   // exchange table for up to M rows on the c
 mmr_status gemm_ln(const void* A16, int64_t lda, const void* W16, int64_t ldw, int M, int K, const float* bias,
                    const float* residual, int64_t ldr, const float* gamma, const float* beta, float eps, void* out16,
                    int64_t ldo16, float* out32, int64_t ldo32, int dtype, cudaStream_t stream);
+
+// same contract, one CTA pair per 256-row block and all 768 columns (gemm_lnrow_sm100.cu); reached through gemm_ln()
+mmr_status gemm_lnrow(const void* A16, int64_t lda, const void* W16, int64_t ldw, int M, int K, const float* bias,
+                      const float* residual, int64_t ldr, const float* gamma, const float* beta, float eps, void* out16,
+                      int64_t ldo16, float* out32, int64_t ldo32, int dtype, cudaStream_t stream);
 
 mmr_status zk_region_sum(const float* feat32, const float* boxes5, const int32_t* label_ids, const float* tables,
                          int vocab, const float* bc1, const float* Wb, const float* bb, void* out16, int rows,

@@ -118,19 +118,21 @@ def test_layernorm():
         assert _rel(acc, 1.0 + ref / 3.0) < 1e-6
 
 
-@pytest.mark.parametrize("kernel", ["tcgen05", "mma_sync", "mma_sync_tma"])
+@pytest.mark.parametrize("kernel", ["tcgen05_pipelined", "tcgen05", "mma_sync", "mma_sync_tma"])
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 def test_attention(dtype, kernel):
-    """All three attention kernels: one CTA per (pair, head) with mma.sync (default: fastest at these sizes), tcgen05 /
-    TMEM with warp-specialised softmax, and the persistent TMA-pipelined mma.sync variant."""
+    """All four attention kernels: tcgen05 / TMEM pipelined four items deep with P kept in TMEM, the first tcgen05
+    version (one item per CTA, P through shared memory), one CTA per (pair, head) with mma.sync, and the persistent
+    TMA-pipelined mma.sync variant."""
     from kddcup_2020_multimodalitiesrecall_2nd_place_b200 import ops, _lib
     lib = _lib.load()
-    _lib.check(lib.mmr_set_tuning(_lib.TUNE_ATTN_TC, 1 if kernel == "tcgen05" else 0))
+    default_tc = lib.mmr_get_tuning(_lib.TUNE_ATTN_TC)
+    _lib.check(lib.mmr_set_tuning(_lib.TUNE_ATTN_TC, {"tcgen05_pipelined": 2, "tcgen05": 1}.get(kernel, 0)))
     _lib.check(lib.mmr_set_tuning(_lib.TUNE_ATTN_TMA, 1 if kernel == "mma_sync_tma" else 0))
     try:
         _attention_cases(dtype, ops)
     finally:
-        _lib.check(lib.mmr_set_tuning(_lib.TUNE_ATTN_TC, 0))
+        _lib.check(lib.mmr_set_tuning(_lib.TUNE_ATTN_TC, default_tc))
         _lib.check(lib.mmr_set_tuning(_lib.TUNE_ATTN_TMA, 0))
 
 
@@ -182,14 +184,26 @@ def test_cast16_is_round_to_nearest_even():
         assert torch.equal(ops.cast16(x, dt), x.to(dt))
 
 
+@pytest.mark.parametrize("variant", [(1, 0), (2, 0), (2, 331), (2, 511), (2, 412), (2, 322)])
 @pytest.mark.parametrize("M,K", [(17408, 768), (17408, 3072), (8192, 768), (300, 768), (1000, 3072), (129, 768)])
-def test_fused_gemm_layernorm(M, K):
-    """One kernel = dense + bias + residual + LayerNorm (cluster of three CTA pairs, DSMEM statistics exchange)
-    against the unfused fp32 reference; in place on the residual stream, ragged M included."""
+def test_fused_gemm_layernorm(M, K, variant):
+    """One kernel = dense + bias + residual + LayerNorm against the unfused fp32 reference; in place on the residual
+    stream, ragged M included.  Variant (1, 0): three CTA pairs per 256-row block meeting through a global table
+    (default); (2, cfg): one pair owns the block and all 768 columns, for every shared-memory split it is built in."""
     from kddcup_2020_multimodalitiesrecall_2nd_place_b200 import ops, _lib
     lib = _lib.load()
     if not lib.mmr_gemm_layernorm_supported(M, K, _lib.DT_FP16):
         pytest.skip("device cannot co-schedule a 6-CTA cluster with this kernel's shared memory")
+    _lib.check(lib.mmr_set_tuning(_lib.TUNE_GEMM_LN, variant[0]))
+    _lib.check(lib.mmr_set_tuning(_lib.TUNE_LN_ROW_CFG, variant[1]))
+    try:
+        _fused_gemm_layernorm_case(M, K, ops)
+    finally:
+        _lib.check(lib.mmr_set_tuning(_lib.TUNE_GEMM_LN, 1))
+        _lib.check(lib.mmr_set_tuning(_lib.TUNE_LN_ROW_CFG, 0))
+
+
+def _fused_gemm_layernorm_case(M, K, ops):
     torch.manual_seed(M + K)
     a = torch.randn(M, K, device="cuda").half()
     w = (torch.randn(768, K, device="cuda") * 0.03).half()
