@@ -134,6 +134,114 @@ zk_region_sum_kernel(const float* __restrict__ feat32, const float* __restrict__
   row_store<E16>(out, out16 + int64_t(row) * kH, nullptr, lane);
 }
 
+// ---- label term, computed once per DISTINCT label phrase of the batch
+// The label term of a box depends on its 8 label token ids only, and a batch holds few distinct phrases (the detector
+// has 33 classes — load_data_v4.py:34-38 — and every padded box carries the all-[PAD] phrase), while the term costs
+// 48 gathered 3 KB table rows per box: 1.3 GB of L1/L2 traffic per 256-pair step, 71 us, when evaluated per box.
+//   claim   one thread per box: hash of the 8 ids -> open-addressing table of {epoch, row}; the first box of a phrase
+//           claims the slot (atomicCAS) and becomes the phrase's representative, the others compare ids and point at it
+//   term    one CTA per representative (the others exit at once): warp w evaluates position w, the eight ReLU'd rows
+//           are summed in position order — the same order, hence the same bits, as zk_region_sum_kernel
+//   sum     zk_region_sum_rep_kernel: feat + term[rep] / 8 + box FC, per box
+// Which box wins a slot is a race; the value it computes is not.  The table is never cleared: entries carry the
+// forward's epoch and older ones count as empty.
+__global__ void __launch_bounds__(256)
+zk_label_claim_kernel(const int32_t* __restrict__ label_ids, int rows, unsigned long long* __restrict__ tab,
+                      uint32_t tab_mask, uint32_t epoch, int32_t* __restrict__ rep) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  const int4* ids4 = reinterpret_cast<const int4*>(label_ids);
+  const int4 a = __ldg(ids4 + 2 * int64_t(row)), b = __ldg(ids4 + 2 * int64_t(row) + 1);
+  uint32_t hsh = 2166136261u;
+  const int32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int t = 0; t < 8; ++t) hsh = (hsh ^ uint32_t(w[t])) * 16777619u;
+  hsh ^= hsh >> 15;
+  uint32_t slot = hsh & tab_mask;
+  const unsigned long long mine = (static_cast<unsigned long long>(epoch) << 32) | uint32_t(row);
+  for (uint32_t probe = 0; probe <= tab_mask; ++probe) {
+    unsigned long long v = *reinterpret_cast<volatile unsigned long long*>(tab + slot);
+    if (uint32_t(v >> 32) != epoch) {            // empty for this forward: try to claim it
+      const unsigned long long old = atomicCAS(tab + slot, v, mine);
+      if (old == v) {
+        rep[row] = row;
+        return;
+      }
+      v = old;                                   // somebody of this forward got there first
+    }
+    const int owner = int(uint32_t(v));
+    const int4 oa = __ldg(ids4 + 2 * int64_t(owner)), ob = __ldg(ids4 + 2 * int64_t(owner) + 1);
+    if (oa.x == a.x && oa.y == a.y && oa.z == a.z && oa.w == a.w && ob.x == b.x && ob.y == b.y && ob.z == b.z &&
+        ob.w == b.w) {
+      rep[row] = owner;
+      return;
+    }
+    slot = (slot + 1) & tab_mask;
+  }
+  rep[row] = row;   // table full (it is sized at <= 25 % load): evaluate the phrase for this box itself
+}
+
+__global__ void __launch_bounds__(256)
+zk_label_term_kernel(const int32_t* __restrict__ label_ids, const float* __restrict__ tables, int vocab,
+                     const float* __restrict__ bc1, const int32_t* __restrict__ rep, float* __restrict__ term32) {
+  __shared__ float s_c[8][kH];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int row = blockIdx.x;
+  if (__ldg(rep + row) != row) return;           // block-uniform
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int ids[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) ids[t] = __ldg(label_ids + int64_t(row) * 8 + t);
+  Row c;
+  row_load(c, bc1, lane);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int j = w - 3 + k;
+    if (j >= 0 && j < 8) row_add(c, tables + (int64_t(k) * vocab + ids[j]) * kH, lane);
+  }
+#pragma unroll
+  for (int i = 0; i < kNV; ++i)
+    *reinterpret_cast<float4*>(&s_c[w][col_of(i, lane)]) =
+        make_float4(fmaxf(c.v[i].x, 0.f), fmaxf(c.v[i].y, 0.f), fmaxf(c.v[i].z, 0.f), fmaxf(c.v[i].w, 0.f));
+  __syncthreads();
+  for (int col = threadIdx.x; col < kH; col += 256) {
+    float acc = 0.f;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) acc += s_c[p][col];      // position order 0..7, as in zk_region_sum_kernel
+    term32[int64_t(row) * kH + col] = acc;
+  }
+}
+
+template <class E16>
+__global__ void __launch_bounds__(256)
+zk_region_sum_rep_kernel(const float* __restrict__ feat32, const float* __restrict__ boxes5,
+                         const int32_t* __restrict__ rep, const float* __restrict__ term32,
+                         const float* __restrict__ Wb, const float* __restrict__ bb,
+                         typename E16::T* __restrict__ out16, int rows) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  Row acc;
+  row_load(acc, term32 + int64_t(__ldg(rep + row)) * kH, lane);
+  Row out;
+  row_load(out, feat32 + int64_t(row) * kH, lane);
+  row_axpy(out, 0.125f, acc);  // mean over the 8 positions
+  row_add(out, bb, lane);
+#pragma unroll
+  for (int d = 0; d < 5; ++d) {
+    const float bx = __ldg(boxes5 + int64_t(row) * 5 + d);
+    Row wrow;
+    row_load(wrow, Wb + d * kH, lane);
+    row_axpy(out, bx, wrow);
+  }
+  row_store<E16>(out, out16 + int64_t(row) * kH, nullptr, lane);
+}
+
 // X0 = LN(concat(E[q], region) + Ttype[seg] + Pos[[0..Lq-1] + [Lq]*R]); also emits the key mask
 // [j < len_query | j - Lq < num_boxes] (model_triple.py:198-201).
 template <class E16>
@@ -414,6 +522,25 @@ mmr_status zk_region_sum(const float* feat32, const float* boxes5, const int32_t
   MMR_DISPATCH16(dtype, ((void)launch_pdl(zk_region_sum_kernel<E16>, dim3(blocks_for(rows)), dim3(256), 0, st, 
                             feat32, boxes5, label_ids, tables, vocab, bc1, Wb, bb,
                             static_cast<typename E16::T*>(out16), rows)));
+  MMR_CUDA_OK(cudaGetLastError());
+  return MMR_OK;
+}
+
+mmr_status zk_label_terms(const int32_t* label_ids, const float* tables, int vocab, const float* bc1,
+                          unsigned long long* tab, uint32_t tab_mask, uint32_t epoch, int32_t* rep, float* term32,
+                          int rows, cudaStream_t st) {
+  (void)launch_pdl(zk_label_claim_kernel, dim3((rows + 255) / 256), dim3(256), 0, st, label_ids, rows, tab, tab_mask,
+                   epoch, rep);
+  MMR_CUDA_OK(cudaGetLastError());
+  (void)launch_pdl(zk_label_term_kernel, dim3(rows), dim3(256), 0, st, label_ids, tables, vocab, bc1,
+                   static_cast<const int32_t*>(rep), term32);
+  MMR_CUDA_OK(cudaGetLastError());
+  return MMR_OK;
+}
+mmr_status zk_region_sum_rep(const float* feat32, const float* boxes5, const int32_t* rep, const float* term32,
+                             const float* Wb, const float* bb, void* out16, int rows, int dtype, cudaStream_t st) {
+  MMR_DISPATCH16(dtype, ((void)launch_pdl(zk_region_sum_rep_kernel<E16>, dim3(blocks_for(rows)), dim3(256), 0, st,
+                            feat32, boxes5, rep, term32, Wb, bb, static_cast<typename E16::T*>(out16), rows)));
   MMR_CUDA_OK(cudaGetLastError());
   return MMR_OK;
 }

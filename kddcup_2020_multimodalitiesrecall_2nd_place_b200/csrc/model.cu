@@ -158,6 +158,11 @@ struct mmr_handle {
   void *f16 = nullptr, *t16 = nullptr, *x16 = nullptr, *qkv16 = nullptr, *ctx16 = nullptr, *h16 = nullptr,
        *pooled16 = nullptr;
   float *tmp32 = nullptr, *x32 = nullptr, *pooled32 = nullptr, *head32 = nullptr, *emb_tap = nullptr;
+  // zk: label term once per distinct phrase (embed.cu): phrase table {epoch, row}, representative of every box, terms
+  unsigned long long* lab_tab = nullptr;
+  uint32_t lab_tab_mask = 0, lab_epoch = 0;
+  int32_t* lab_rep = nullptr;
+  float* lab_term32 = nullptr;
   float* layer_tap = nullptr;   // [n_layers, rows_max, hidden], allocated by mmr_set_debug_taps(h, 2)
   int32_t* key_mask = nullptr;
   int64_t rows_max = 0;   // encoder rows at max_batch
@@ -486,6 +491,14 @@ static mmr_status alloc_workspace(mmr_handle* h) {
   add(B * H * 4);               // pooled32
   add(B * 2 * H * 4);           // head32
   add(M * H * 4);               // emb_tap
+  uint32_t lab_slots = 0;
+  if (c.model_kind == MMR_MODEL_IMAGEBERT_ZK) {
+    lab_slots = 1024;
+    while (lab_slots < 4 * uint64_t(B * R)) lab_slots <<= 1;   // <= 25 % load
+    add(size_t(lab_slots) * 8);   // lab_tab
+    add(B * R * 4);               // lab_rep
+    add(B * R * H * 4);           // lab_term32
+  }
   bytes += 4096;
   MMR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->work.base), bytes));
   h->work.cap = bytes;
@@ -503,6 +516,14 @@ static mmr_status alloc_workspace(mmr_handle* h) {
   h->head32 = static_cast<float*>(h->work.take(B * 2 * H * 4));
   h->emb_tap = static_cast<float*>(h->work.take(M * H * 4));
   if (!h->emb_tap) return fail(MMR_ERR_NOMEM, "workspace arena mis-sized");
+  if (lab_slots != 0) {
+    h->lab_tab = static_cast<unsigned long long*>(h->work.take(size_t(lab_slots) * 8));
+    h->lab_rep = static_cast<int32_t*>(h->work.take(B * R * 4));
+    h->lab_term32 = static_cast<float*>(h->work.take(B * R * H * 4));
+    if (!h->lab_term32) return fail(MMR_ERR_NOMEM, "workspace arena mis-sized (label terms)");
+    h->lab_tab_mask = lab_slots - 1;
+    MMR_CUDA_OK(cudaMemset(h->lab_tab, 0, size_t(lab_slots) * 8));   // epoch 0 = never written
+  }
   return MMR_OK;
 }
 
@@ -615,8 +636,19 @@ static mmr_status forward_single_stream(Ctx& c, const mmr_inputs* in, int B, flo
     } else {
       // feat = ReLU(f . Wc2 + bc2)  (model_triple.py:192-194)
       MMR_TRY(c.G(h->f16, cfg.feat_dim, h->conv2, B * R, nullptr, nullptr, 0, h->tmp32, MMR_ACT_RELU));
-      MMR_TRY(zk_region_sum(h->tmp32, in->boxes, in->label_ids, h->tables, cfg.vocab, h->bc1, h->Wb, h->bb, h->t16,
-                            B * R, c.dt, c.st));
+      // (the claim kernel reads the 8 ids of a box as two 16-byte words)
+      if (tuning(MMR_TUNE_LABEL_DEDUP) != 0 && (reinterpret_cast<uintptr_t>(in->label_ids) & 15) == 0) {
+        if (++h->lab_epoch == 0) h->lab_epoch = 1;
+        MMR_TRY(zk_label_terms(in->label_ids, h->tables, cfg.vocab, h->bc1, h->lab_tab, h->lab_tab_mask, h->lab_epoch,
+                               h->lab_rep, h->lab_term32, B * R, c.st));
+        MMR_TRY(c.mark(K_ROW, 0));
+        MMR_TRY(c.mark(K_ROW, 0));
+        MMR_TRY(zk_region_sum_rep(h->tmp32, in->boxes, h->lab_rep, h->lab_term32, h->Wb, h->bb, h->t16, B * R, c.dt,
+                                  c.st));
+      } else {
+        MMR_TRY(zk_region_sum(h->tmp32, in->boxes, in->label_ids, h->tables, cfg.vocab, h->bc1, h->Wb, h->bb, h->t16,
+                              B * R, c.dt, c.st));
+      }
       MMR_TRY(c.mark(K_ROW, 0));
     }
     // region = (label + box + feat) . Wfe + bfe  (pixelbert.py:449-452)

@@ -260,3 +260,35 @@ def test_cfg5_three_model_ensemble_topk_against_oracle():
             assert top_g[q] == top_o[q], q
         else:
             assert len(set(top_g[q]) & set(top_o[q])) >= 4
+
+
+@pytest.mark.parametrize("phrases", ["pool", "all_distinct", "one"])
+def test_zk_label_term_once_per_phrase_is_bit_identical(phrases):
+    """The zk label-text term evaluated once per distinct label phrase of the batch (hash claim + representative +
+    per-box sum) gives the same bits as the per-box evaluation: few phrases (the synthetic pool), every box its own
+    phrase (no sharing, worst case for the table), and one phrase for all boxes (every box races for one slot)."""
+    from kddcup_2020_multimodalitiesrecall_2nd_place_b200 import _lib
+    lib = _lib.load()
+    cfg = ModelConfig(ZK, n_layers=1, lq=20, nbox=10, vocab=2000)
+    w = synth.make_weights(cfg, seed=synth.SEED0 + 9)
+    B = 96
+    inp = synth.make_inputs(cfg, B, seed=synth.SEED0 + 9, n_queries=4)
+    rng = np.random.default_rng(7)
+    ids = np.array(inp["label_ids"], copy=True)
+    if phrases == "all_distinct":
+        ids = rng.integers(1, cfg.vocab, size=ids.shape).astype(ids.dtype)
+    elif phrases == "one":
+        ids[...] = ids.reshape(-1, 8)[0]
+    inp = dict(inp, label_ids=ids)
+    sc = _scorer(cfg, w, B)
+    try:
+        out = {}
+        for dedup in (1, 0):
+            _lib.check(lib.mmr_set_tuning(_lib.TUNE_LABEL_DEDUP, dedup))
+            for rep in range(2):   # twice: the phrase table is reused across forwards (epoch tags)
+                out[dedup], _ = _gpu_probs(sc, inp)
+        assert torch.equal(out[0], out[1])
+        assert (out[1] - _oracle(cfg, w, inp)["probs"]).abs().max().item() <= TOL
+    finally:
+        _lib.check(lib.mmr_set_tuning(_lib.TUNE_LABEL_DEDUP, 1))
+        sc.close()
