@@ -293,7 +293,7 @@ def main():
         except Exception:
             pass
         try:
-            ncu = json.load(open(os.path.join(ROOT, "profiles", "r01k_gemm_ncu_summary.json")))["kernels"]
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "r01m_gemm_ncu_summary.json")))["kernels"]
         except Exception:
             pass
         peak = peaks.get("bf16_tflops_sustained") or 1400.0
@@ -315,7 +315,7 @@ def main():
         roofline = {
             "bound": "tensor", "kernel": "gemm_pair16_kernel (QKV and FFN-in projections, 16-bit output, TMA-store epilogue)",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-            "traffic_source": "profiles/r01k_gemm_ncu_summary.json (dram read+write, mean of the two shapes)" if traffic else None,
+            "traffic_source": "profiles/r01m_gemm_ncu_summary.json (dram read+write, mean of the two shapes)" if traffic else None,
             "peak_source": peak_src, "launches_per_step": d_n // n_prof, "avg_launch_us": d_ms / d_n * 1e3,
             "flops_per_launch": d_fl / d_n,
             "timing": "CUDA events recorded by the library after every launch on the forward's stream, 5 profiled steps "
