@@ -33,11 +33,15 @@ constexpr int kLnN = 768;
 constexpr int kLnTiles = kLnN / kBN;            // 3 column tiles = 3 pairs per group
 // the warp arbiter favours higher warp ids: the two latency-critical single-thread roles get ids 8 and 9
 constexpr int kLnProducerWarp = kEpiWarps, kLnMmaWarp = kEpiWarps + 1;
-// Shared-memory split between the operand ring and the epilogue, per K:
-//   K <= 1024 (out-projection): the launch is bound by its epilogue (tools/ln_trace.py), so 3 operand stages and a
-//     3-slot residual / fp32-staging ring + 1 16-bit stage per warp (what fits beside them): three of the four residual chunks of a tile are
-//     in flight before the accumulator is even complete;
-//   larger K (FFN-out): MMA-bound, 4 operand stages, 2 slots + 1 16-bit stage per warp.
+// Shared-memory split between the operand ring and the epilogue, per K (chosen by A/B runs of the whole 12-layer
+// forward, three alternations on one box):
+//   K <= 1024 (out-projection): 4 operand stages, a 2-slot residual / fp32-staging ring + 1 16-bit stage per warp.
+//     The launch is bound by its epilogue chain (tools/ln_trace.py), but with 3 stages its main loop is
+//     load-latency-bound as well (7 us per tile instead of 4.4, measured in gemm_lnrow_sm100.cu), which delays the
+//     first tile of every pair; 3 stages + 3 slots measured 0.6 % slower over the forward.
+//   larger K (FFN-out): MMA-bound (23 us of MMAs per tile against a 12 us epilogue that hides behind them), so the
+//     operand ring gets everything: 5 stages, ONE slot + 1 16-bit stage per warp (the residual chunks then arrive
+//     one at a time, still inside the MMA time).  4 stages + 2 slots measured 1.6 % slower over the forward.
 template <int STAGES, int SLOTS, int O16>
 struct LnCfg {
   static constexpr int kStages = STAGES, kSlots = SLOTS, kO16 = O16;
@@ -48,8 +52,8 @@ struct LnCfg {
   static constexpr size_t kSmemBytes =
       1024 + PairRing<STAGES>::kOperandBytes + size_t(kEpiWarps) * kWarpBytes + 3 * kBN * 4 + 512;
 };
-using LnCfgShortK = LnCfg<3, 3, 1>;
-using LnCfgLongK = LnCfg<4, 2, 1>;
+using LnCfgShortK = LnCfg<4, 2, 1>;
+using LnCfgLongK = LnCfg<5, 1, 1>;
 constexpr int kLnSlots = 2 * kLnTiles;          // partial statistics per row: 3 column tiles x 2 halves
 
 struct GemmLnParams {
