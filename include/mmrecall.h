@@ -77,10 +77,13 @@ int mmr_abi_version(void);
  *                                                            three digits (operand stages, fp32 chunk slots, 16-bit
  *                                                            stages per epilogue warp): 421, 331, 511, 412, 322; 0 = default 
  *   MMR_TUNE_LABEL_DEDUP   (env MMR_LABEL_DEDUP,  default 1) zk label-text term evaluated once per distinct label phrase
- *                                                            of the batch (bit-identical to the per-box evaluation, 0) */
+ *                                                            of the batch (bit-identical to the per-box evaluation, 0) 
+ *   MMR_TUNE_LX_MERGE      (env MMR_LX_MERGE,     default 1) LXMERT: the projections of the language and the visual
+ *                                                            stream (different weights, one activation buffer) as ONE
+ *                                                            launch each when batch x query length is a multiple of 256 */
 enum { MMR_TUNE_GEMM_PAIR = 0, MMR_TUNE_GEMM_P16 = 1, MMR_TUNE_GEMM_TAIL = 2, MMR_TUNE_GEMM_CLUSTER = 3,
        MMR_TUNE_GEMM_LN = 4, MMR_TUNE_PDL = 5, MMR_TUNE_ATTN_TMA = 6, MMR_TUNE_ATTN_TC = 7, MMR_TUNE_LN_ROW_CFG = 8,
-       MMR_TUNE_LABEL_DEDUP = 9, MMR_TUNE_COUNT = 10 };
+       MMR_TUNE_LABEL_DEDUP = 9, MMR_TUNE_LX_MERGE = 10, MMR_TUNE_COUNT = 11 };
 mmr_status mmr_set_tuning(int knob, int value);
 /* Current value of a knob (-1 for an unknown one). */
 int mmr_get_tuning(int knob);

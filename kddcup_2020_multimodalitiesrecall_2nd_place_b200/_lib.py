@@ -11,7 +11,7 @@ MMR_OK = 0
 DT_FP16, DT_BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_GELU_TANH, ACT_GELU_ERF, ACT_TANH = range(5)
 MODEL_ZK, MODEL_LDS, MODEL_LXMERT = range(3)
-TUNE_GEMM_PAIR, TUNE_GEMM_P16, TUNE_GEMM_TAIL, TUNE_GEMM_CLUSTER, TUNE_GEMM_LN, TUNE_PDL, TUNE_ATTN_TMA, TUNE_ATTN_TC, TUNE_LN_ROW_CFG, TUNE_LABEL_DEDUP = range(10)
+TUNE_GEMM_PAIR, TUNE_GEMM_P16, TUNE_GEMM_TAIL, TUNE_GEMM_CLUSTER, TUNE_GEMM_LN, TUNE_PDL, TUNE_ATTN_TMA, TUNE_ATTN_TC, TUNE_LN_ROW_CFG, TUNE_LABEL_DEDUP, TUNE_LX_MERGE = range(11)
 
 # every symbol include/mmrecall.h declares (tests check the .so exports all of them)
 EXPORTS = [

@@ -37,6 +37,8 @@ constexpr size_t p16_smem_bytes() {
 struct P16Params {
   int M, N, K;
   const float* bias;     // [N] or null
+  const float* bias2;    // bias of the SECOND weight matrix (row blocks >= split_blk), or null
+  int split_blk;         // first 256-row block that multiplies the second weight matrix (INT_MAX: one matrix)
   uint32_t idesc_fmt;    // 0 fp16 / 1 bf16
   int full_tiles;        // work items [0, full_tiles) are 256 columns wide; the rest are the split tail
   int tail_split_log2;   // 0, 1 or 2: tail items are (256 >> s) columns wide
@@ -75,7 +77,8 @@ __device__ __forceinline__ TileCoord p16_tile(const P16Params& p, int tile, int 
 template <int ACT, class E16, int STAGES, int CP>
 __global__ void __cluster_dims__(2 * CP, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_pair16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                   const __grid_constant__ CUtensorMap tmap_w_tail, const __grid_constant__ CUtensorMap tmap_o,
+                   const __grid_constant__ CUtensorMap tmap_w_tail, const __grid_constant__ CUtensorMap tmap_w2,
+                   const __grid_constant__ CUtensorMap tmap_w2_tail, const __grid_constant__ CUtensorMap tmap_o,
                    const P16Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -102,6 +105,8 @@ gemm_pair16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_w);
     tma_prefetch_desc(&tmap_w_tail);
+    tma_prefetch_desc(&tmap_w2);
+    tma_prefetch_desc(&tmap_w2_tail);
     tma_prefetch_desc(&tmap_o);
     ring.init(2 * kEpiWarps, CP);
     fence_mbar_init();
@@ -125,7 +130,10 @@ gemm_pair16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       for (int tile = pair; tile < total_tiles; tile += n_pairs) {
         const TileCoord t = p16_tile(p, tile, n_tiles);
         const int w_rows = t.bn / 2;
-        pair_produce_tile<STAGES, CP>(ring, pos, &tmap_a, t.bn == kBN ? &tmap_w : &tmap_w_tail,
+        // two weight matrices over one row range (LXMERT: language rows, then visual rows): chosen by the row block
+        const bool second = t.m_blk >= p.split_blk;
+        pair_produce_tile<STAGES, CP>(ring, pos, &tmap_a,
+                                      t.bn == kBN ? (second ? &tmap_w2 : &tmap_w) : (second ? &tmap_w2_tail : &tmap_w_tail),
                                       (t.m_blk * CP + int(cpair)) * kPairRows + int(rank) * kCtaRows,
                                       t.col0 + int(rank) * w_rows, w_rows, k_blocks, rank, leader, cpair);
       }
@@ -163,6 +171,7 @@ gemm_pair16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     for (int tile = pair; tile < total_tiles; tile += n_pairs, ++it) {
       const TileCoord t = p16_tile(p, tile, n_tiles);
       const int acc = it & 1;
+      const float* bias = t.m_blk >= p.split_blk ? p.bias2 : p.bias;
       const int wcols = t.bn / 2;                       // columns owned by this warp: 128, 64 or 32
       const int wcol0 = t.col0 + half * wcols;
       const int n_chunks = wcols / 32;                  // 4, 2 or 1
@@ -178,7 +187,7 @@ gemm_pair16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         float4 bb[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          bb[j] = p.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(p.bias + wcol0 + c * 32 + 4 * j))
+          bb[j] = bias != nullptr ? __ldg(reinterpret_cast<const float4*>(bias + wcol0 + c * 32 + 4 * j))
                                     : make_float4(0.f, 0.f, 0.f, 0.f);
         uint32_t r[32];
         tmem_ld_32x32(taddr + uint32_t(c * 32), r);
@@ -232,22 +241,24 @@ gemm_pair16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 
 template <int ACT, class E16, int STAGES, int CP>
 static mmr_status launch_p16s(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& twt,
-                              const CUtensorMap& to, const P16Params& p, int grid, cudaStream_t stream) {
+                              const CUtensorMap& tw2, const CUtensorMap& twt2, const CUtensorMap& to,
+                              const P16Params& p, int grid, cudaStream_t stream) {
   auto kern = gemm_pair16_kernel<ACT, E16, STAGES, CP>;
   static bool configured = false;
   if (!configured) {
     MMR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(p16_smem_bytes<STAGES>())));
     configured = true;
   }
-  MMR_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(kGemmThreads), p16_smem_bytes<STAGES>(), stream, ta, tw, twt, to, p));
+  MMR_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(kGemmThreads), p16_smem_bytes<STAGES>(), stream, ta, tw, twt, tw2, twt2, to, p));
   return MMR_OK;
 }
 constexpr int kP16Stages = 6;
 template <int ACT, class E16>
-static mmr_status launch_p16(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& twt, const CUtensorMap& to,
-                             const P16Params& p, int grid, int cluster_pairs, cudaStream_t stream) {
-  if (cluster_pairs == 2) return launch_p16s<ACT, E16, kP16Stages, 2>(ta, tw, twt, to, p, grid, stream);
-  return launch_p16s<ACT, E16, kP16Stages, 1>(ta, tw, twt, to, p, grid, stream);
+static mmr_status launch_p16(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& twt, const CUtensorMap& tw2,
+                             const CUtensorMap& twt2, const CUtensorMap& to, const P16Params& p, int grid,
+                             int cluster_pairs, cudaStream_t stream) {
+  if (cluster_pairs == 2) return launch_p16s<ACT, E16, kP16Stages, 2>(ta, tw, twt, tw2, twt2, to, p, grid, stream);
+  return launch_p16s<ACT, E16, kP16Stages, 1>(ta, tw, twt, tw2, twt2, to, p, grid, stream);
 }
 
 // Co-resident 4-CTA clusters of this kernel on the current device (0: none).  All instantiations share the launch
@@ -282,13 +293,14 @@ static int p16_max_quads() {
 
 template <class E16>
 static mmr_status dispatch_p16(int act, const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& twt,
-                               const CUtensorMap& to, const P16Params& p, int grid, int cp, cudaStream_t s) {
+                               const CUtensorMap& tw2, const CUtensorMap& twt2, const CUtensorMap& to,
+                               const P16Params& p, int grid, int cp, cudaStream_t s) {
   switch (act) {
-    case MMR_ACT_NONE: return launch_p16<MMR_ACT_NONE, E16>(ta, tw, twt, to, p, grid, cp, s);
-    case MMR_ACT_RELU: return launch_p16<MMR_ACT_RELU, E16>(ta, tw, twt, to, p, grid, cp, s);
-    case MMR_ACT_GELU_TANH: return launch_p16<MMR_ACT_GELU_TANH, E16>(ta, tw, twt, to, p, grid, cp, s);
-    case MMR_ACT_GELU_ERF: return launch_p16<MMR_ACT_GELU_ERF, E16>(ta, tw, twt, to, p, grid, cp, s);
-    case MMR_ACT_TANH: return launch_p16<MMR_ACT_TANH, E16>(ta, tw, twt, to, p, grid, cp, s);
+    case MMR_ACT_NONE: return launch_p16<MMR_ACT_NONE, E16>(ta, tw, twt, tw2, twt2, to, p, grid, cp, s);
+    case MMR_ACT_RELU: return launch_p16<MMR_ACT_RELU, E16>(ta, tw, twt, tw2, twt2, to, p, grid, cp, s);
+    case MMR_ACT_GELU_TANH: return launch_p16<MMR_ACT_GELU_TANH, E16>(ta, tw, twt, tw2, twt2, to, p, grid, cp, s);
+    case MMR_ACT_GELU_ERF: return launch_p16<MMR_ACT_GELU_ERF, E16>(ta, tw, twt, tw2, twt2, to, p, grid, cp, s);
+    case MMR_ACT_TANH: return launch_p16<MMR_ACT_TANH, E16>(ta, tw, twt, tw2, twt2, to, p, grid, cp, s);
     default: return fail(MMR_ERR_INVALID, "mmr_gemm: unknown activation %d", act);
   }
 }
@@ -299,11 +311,15 @@ bool gemm_pair16_eligible(int M, int N, int K, const float* residual, const void
          out16 != nullptr;
 }
 
-// Arguments are already validated by mmr::gemm.
-mmr_status gemm_pair16(const void* A16, int64_t lda, const void* W16, int64_t ldw, int M, int N, int K,
-                       const float* bias, void* out16, int64_t ldo16, int act, int dtype, cudaStream_t stream) {
+// Arguments are already validated by mmr::gemm.  W16b / biasb / split_row: optional SECOND weight matrix (same N, K,
+// ldw) for the rows from split_row on (a multiple of 256) — LXMERT's language and visual streams, which share the
+// activation buffers but not the weights, then run their projection as ONE launch with full waves.
+mmr_status gemm_pair16_2w(const void* A16, int64_t lda, const void* W16, const void* W16b, int64_t ldw, int M, int N,
+                          int K, const float* bias, const float* biasb, int split_row, void* out16, int64_t ldo16,
+                          int act, int dtype, cudaStream_t stream) {
+  const bool two = W16b != nullptr;
   const bool split_tail = tuning(MMR_TUNE_GEMM_TAIL) != 0;
-  const int want_cp = tuning(MMR_TUNE_GEMM_CLUSTER);
+  const int want_cp = two ? 1 : tuning(MMR_TUNE_GEMM_CLUSTER);   // a 4-CTA cluster spans two row blocks
   const int m_tiles = (M + kPairRows - 1) / kPairRows, n_tiles = N / kBN;
   // 4-CTA clusters (two pairs sharing the W tile) when the device places enough of them and there are at least two
   // row blocks; else lone pairs
@@ -311,7 +327,8 @@ mmr_status gemm_pair16(const void* A16, int64_t lda, const void* W16, int64_t ld
   const int cp = (quads >= 8 && m_tiles >= 2) ? 2 : 1;
   const int units = cp == 2 ? quads : sm_count() / 2;            // clusters that run concurrently
   const int items = ((m_tiles + cp - 1) / cp) * n_tiles;
-  P16Params p{M, N, K, bias, uint32_t(dtype), items, 0, items, g_p16_trace};
+  P16Params p{M, N, K, bias, two ? biasb : bias, two ? split_row / kPairRows : 0x7fffffff, uint32_t(dtype), items, 0,
+              items, g_p16_trace};
   const int rem = items % units;
   if (split_tail && items > units && rem != 0) {
     // split the last partial wave so that it fills (at most) all clusters once
@@ -323,14 +340,20 @@ mmr_status gemm_pair16(const void* A16, int64_t lda, const void* W16, int64_t ld
       p.total_items = p.full_tiles + (rem << s);
     }
   }
-  CUtensorMap ta, tw, twt, to;
+  CUtensorMap ta, tw, twt, tw2, twt2, to;
   MMR_TRY(make_tmap_2d(&ta, A16, M, K, lda, kCtaRows, dtype));
   MMR_TRY(make_tmap_2d(&tw, W16, N, K, ldw, kBN / 2 / cp, dtype));
   MMR_TRY(make_tmap_2d(&twt, W16, N, K, ldw, (kBN >> p.tail_split_log2) / 2 / cp, dtype));
+  MMR_TRY(make_tmap_2d(&tw2, two ? W16b : W16, N, K, ldw, kBN / 2 / cp, dtype));
+  MMR_TRY(make_tmap_2d(&twt2, two ? W16b : W16, N, K, ldw, (kBN >> p.tail_split_log2) / 2 / cp, dtype));
   MMR_TRY(make_tmap_ex(&to, out16, M, N, ldo16, dtype == MMR_DT_BF16 ? 1 : 0, 32, 32, 64));
   const int grid = 2 * cp * (p.total_items < units ? p.total_items : units);
-  if (dtype == MMR_DT_BF16) return dispatch_p16<BF16>(act, ta, tw, twt, to, p, grid, cp, stream);
-  return dispatch_p16<FP16>(act, ta, tw, twt, to, p, grid, cp, stream);
+  if (dtype == MMR_DT_BF16) return dispatch_p16<BF16>(act, ta, tw, twt, tw2, twt2, to, p, grid, cp, stream);
+  return dispatch_p16<FP16>(act, ta, tw, twt, tw2, twt2, to, p, grid, cp, stream);
+}
+mmr_status gemm_pair16(const void* A16, int64_t lda, const void* W16, int64_t ldw, int M, int N, int K,
+                       const float* bias, void* out16, int64_t ldo16, int act, int dtype, cudaStream_t stream) {
+  return gemm_pair16_2w(A16, lda, W16, nullptr, ldw, M, N, K, bias, nullptr, 0, out16, ldo16, act, dtype, stream);
 }
 
 }  // namespace mmr

@@ -144,4 +144,9 @@ bool gemm_pair16_eligible(int M, int N, int K, const float* residual, const void
 mmr_status gemm_pair16(const void* A16, int64_t lda, const void* W16, int64_t ldw, int M, int N, int K,
                        const float* bias, void* out16, int64_t ldo16, int act, int dtype, cudaStream_t stream);
 
+// the same with a second weight matrix for the rows from split_row on (see gemm16_sm100.cu)
+mmr_status gemm_pair16_2w(const void* A16, int64_t lda, const void* W16, const void* W16b, int64_t ldw, int M, int N,
+                          int K, const float* bias, const float* biasb, int split_row, void* out16, int64_t ldo16,
+                          int act, int dtype, cudaStream_t stream);
+
 }  // namespace mmr

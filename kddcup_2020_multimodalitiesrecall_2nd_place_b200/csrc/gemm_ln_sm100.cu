@@ -50,7 +50,7 @@ struct LnCfg {
   // their buffers when the next chunk starts writing (slot reuse distance SLOTS, 16-bit stage reuse distance O16)
   static constexpr int kPending = (2 * SLOTS - 2) < (2 * O16 - 1) ? (2 * SLOTS - 2) : (2 * O16 - 1);
   static constexpr size_t kSmemBytes =
-      1024 + PairRing<STAGES>::kOperandBytes + size_t(kEpiWarps) * kWarpBytes + 3 * kBN * 4 + 512;
+      1024 + PairRing<STAGES>::kOperandBytes + size_t(kEpiWarps) * kWarpBytes + 2 * 3 * kBN * 4 + 512;
 };
 using LnCfgShortK = LnCfg<4, 2, 1>;
 using LnCfgLongK = LnCfg<5, 1, 1>;
@@ -61,6 +61,12 @@ struct GemmLnParams {
   const float* bias;      // [768]
   const float* gamma;     // [768]
   const float* beta;      // [768]
+  // second parameter set, for the row blocks >= split_blk (LXMERT: language rows, then visual rows, one launch);
+  // equal to the first when the launch has one weight matrix
+  const float* bias2;
+  const float* gamma2;
+  const float* beta2;
+  int split_blk;
   float eps;
   uint4* stats;           // [m_tiles][6][256]  {mean_i, tag, M2_i, tag}: each half is one 8-byte store carrying its flag
   uint32_t* epoch;        // [0] tag of this launch (read at kernel start), [1] CTAs finished; the last CTA bumps [0]
@@ -82,14 +88,15 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 template <class E16, class CFG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-               const __grid_constant__ CUtensorMap tmap_r, const __grid_constant__ CUtensorMap tmap_o32,
-               const __grid_constant__ CUtensorMap tmap_o16, const GemmLnParams p) {
+               const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_r,
+               const __grid_constant__ CUtensorMap tmap_o32, const __grid_constant__ CUtensorMap tmap_o16,
+               const GemmLnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int kLnStages = CFG::kStages, kSlots = CFG::kSlots, kO16 = CFG::kO16;
   uint8_t* epi = smem + PairRing<kLnStages>::kOperandBytes;                       // 1024-aligned
-  float* vec_s = reinterpret_cast<float*>(epi + size_t(kEpiWarps) * CFG::kWarpBytes);   // [3][256]: bias, gamma, beta
-  uint64_t* bars = reinterpret_cast<uint64_t*>(vec_s + 3 * kBN);
+  float* vec_s = reinterpret_cast<float*>(epi + size_t(kEpiWarps) * CFG::kWarpBytes);   // [2 sets][3][256]: bias, gamma, beta
+  uint64_t* bars = reinterpret_cast<uint64_t*>(vec_s + 2 * 3 * kBN);
   PairRing<kLnStages> ring;
   ring.carve(smem, bars);
   uint64_t* res_bar = bars + PairRing<kLnStages>::kNumBars;    // [8 warps][kSlots] residual chunk landed
@@ -108,6 +115,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == kLnProducerWarp && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_w2);
     tma_prefetch_desc(&tmap_r);
     tma_prefetch_desc(&tmap_o32);
     tma_prefetch_desc(&tmap_o16);
@@ -120,9 +128,11 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tmem_relinquish_2sm();
   }
   // this pair's column tile never changes: its bias / gamma / beta slices live in shared memory for the whole kernel
-  for (int i = threadIdx.x; i < 3 * kBN; i += kGemmThreads) {
-    const float* src = i < kBN ? p.bias : (i < 2 * kBN ? p.gamma : p.beta);
-    vec_s[i] = __ldg(src + n_tile * kBN + (i & (kBN - 1)));
+  for (int i = threadIdx.x; i < 2 * 3 * kBN; i += kGemmThreads) {
+    const int set = i / (3 * kBN), j = i % (3 * kBN);
+    const float* src = set == 0 ? (j < kBN ? p.bias : (j < 2 * kBN ? p.gamma : p.beta))
+                                : (j < kBN ? p.bias2 : (j < 2 * kBN ? p.gamma2 : p.beta2));
+    vec_s[i] = __ldg(src + n_tile * kBN + (j & (kBN - 1)));
   }
   tc_fence_before();
   __syncthreads();
@@ -139,8 +149,8 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       RingPos pos;
       const int w_row = n_tile * kBN + int(rank) * (kBN / 2);
       for (int m_blk = group; m_blk < m_tiles; m_blk += n_groups)
-        pair_produce_tile<kLnStages, 1>(ring, pos, &tmap_a, &tmap_w, m_blk * kPairRows + int(rank) * kCtaRows, w_row,
-                                        kBN / 2, k_blocks, rank, 0, 0);
+        pair_produce_tile<kLnStages, 1>(ring, pos, &tmap_a, m_blk >= p.split_blk ? &tmap_w2 : &tmap_w,
+                                        m_blk * kPairRows + int(rank) * kCtaRows, w_row, kBN / 2, k_blocks, rank, 0, 0);
     }
   } else if (warp == kLnMmaWarp) {
     // ===================== MMA issuer (pair leader, one thread) =====================
@@ -162,9 +172,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint8_t* wbuf = epi + size_t(ew) * CFG::kWarpBytes;
     // wbuf + 4096 s               : fp32 slot s    [32 rows x 32 cols], 128-byte swizzle
     // wbuf + 4096 kSlots + 2048 t : 16-bit stage t [32 rows x 32 cols], 64-byte swizzle
-    const float* bias_w = vec_s + half * 128;             // this warp's 128 columns of the three vectors
-    const float* gamma_w = vec_s + kBN + half * 128;
-    const float* beta_w = vec_s + 2 * kBN + half * 128;
+    const float* vec_w = vec_s + half * 128;               // this warp's 128 columns of the three vectors, set 0
     uint64_t* rfull = res_bar + kSlots * ew;
     const uint32_t tag = tag_of_launch;   // this launch's flag value (never 0)
     const uint32_t tempty_leader0 = mapa_u32(smem_u32(&ring.tempty[0]), 0);
@@ -176,6 +184,9 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     int it = 0;
     for (int m_blk = group; m_blk < m_tiles; m_blk += n_groups, ++it) {
       const int acc = it & 1;
+      const float* bias_w = vec_w + (m_blk >= p.split_blk ? 3 * kBN : 0);
+      const float* gamma_w = bias_w + kBN;
+      const float* beta_w = bias_w + 2 * kBN;
       const int row0 = m_blk * kPairRows + row_in_blk;
       const uint32_t taddr = tmem_base + uint32_t(acc) * kBN + (uint32_t(quarter * 32) << 16) + uint32_t(half * 128);
 
@@ -415,53 +426,69 @@ bool gemm_ln_eligible(int M, int N, int K, int dtype) {
 }
 
 template <class E16, class CFG>
-static mmr_status launch_ln_cfg(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tr,
+static mmr_status launch_ln_cfg(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tw2, const CUtensorMap& tr,
                                 const CUtensorMap& to32, const CUtensorMap& to16, const GemmLnParams& p,
                                 cudaStream_t stream) {
   const int m_tiles = (p.M + kPairRows - 1) / kPairRows;
   const int max_groups = ln_max_pairs<E16, CFG>() / kLnTiles;
   const int groups = m_tiles < max_groups ? m_tiles : max_groups;
   MMR_CUDA_OK(launch_pdl(gemm_ln_kernel<E16, CFG>, dim3(2 * kLnTiles * groups), dim3(kGemmThreads), CFG::kSmemBytes,
-                         stream, ta, tw, tr, to32, to16, p));
+                         stream, ta, tw, tw2, tr, to32, to16, p));
   return MMR_OK;
 }
 template <class E16>
-static mmr_status launch_ln(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tr, const CUtensorMap& to32,
-                            const CUtensorMap& to16, const GemmLnParams& p, cudaStream_t stream) {
-  if (p.K <= 1024) return launch_ln_cfg<E16, LnCfgShortK>(ta, tw, tr, to32, to16, p, stream);
-  return launch_ln_cfg<E16, LnCfgLongK>(ta, tw, tr, to32, to16, p, stream);
+static mmr_status launch_ln(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tw2, const CUtensorMap& tr,
+                            const CUtensorMap& to32, const CUtensorMap& to16, const GemmLnParams& p, cudaStream_t stream) {
+  if (p.K <= 1024) return launch_ln_cfg<E16, LnCfgShortK>(ta, tw, tw2, tr, to32, to16, p, stream);
+  return launch_ln_cfg<E16, LnCfgLongK>(ta, tw, tw2, tr, to32, to16, p, stream);
 }
 
-mmr_status gemm_ln(const void* A16, int64_t lda, const void* W16, int64_t ldw, int M, int K, const float* bias,
-                   const float* residual, int64_t ldr, const float* gamma, const float* beta, float eps, void* out16,
-                   int64_t ldo16, float* out32, int64_t ldo32, int dtype, cudaStream_t stream) {
+// W16b / biasb / gammab / betab / split_row: optional SECOND parameter set for the rows from split_row on (a multiple
+// of 256): LXMERT's two streams share the activation buffers, so their projection + LayerNorm tails run as one launch.
+mmr_status gemm_ln_2w(const void* A16, int64_t lda, const void* W16, const void* W16b, int64_t ldw, int M, int K,
+                      const float* bias, const float* biasb, const float* residual, int64_t ldr, const float* gamma,
+                      const float* gammab, const float* beta, const float* betab, int split_row, float eps, void* out16,
+                      int64_t ldo16, float* out32, int64_t ldo32, int dtype, cudaStream_t stream) {
   MMR_TRY(require_sm100());
+  const bool two = W16b != nullptr;
   MMR_REQUIRE(A16 && W16 && bias && residual && gamma && beta && out16 && out32, "gemm_ln: null argument");
+  MMR_REQUIRE(!two || (biasb && gammab && betab && split_row > 0 && split_row % kPairRows == 0),
+              "gemm_ln: second parameter set incomplete or split row %d not a multiple of %d", split_row, kPairRows);
   MMR_REQUIRE(gemm_ln_eligible(M, kLnN, K, dtype), "gemm_ln: shape M=%d K=%d not eligible", M, K);
   MMR_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && ldr % 4 == 0 && ldo32 % 4 == 0 && ldo16 % 8 == 0,
               "gemm_ln: row strides break 16-byte alignment");
-  MMR_REQUIRE(((reinterpret_cast<uintptr_t>(A16) | reinterpret_cast<uintptr_t>(W16) | reinterpret_cast<uintptr_t>(residual) |
-                reinterpret_cast<uintptr_t>(out16) | reinterpret_cast<uintptr_t>(out32) | reinterpret_cast<uintptr_t>(bias) |
-                reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0,
+  MMR_REQUIRE(((reinterpret_cast<uintptr_t>(A16) | reinterpret_cast<uintptr_t>(W16) | reinterpret_cast<uintptr_t>(W16b) |
+                reinterpret_cast<uintptr_t>(residual) | reinterpret_cast<uintptr_t>(out16) |
+                reinterpret_cast<uintptr_t>(out32) | reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(gamma) |
+                reinterpret_cast<uintptr_t>(beta) | reinterpret_cast<uintptr_t>(biasb) | reinterpret_cast<uintptr_t>(gammab) |
+                reinterpret_cast<uintptr_t>(betab)) & 15) == 0,
               "gemm_ln: pointers must be 16-byte aligned");
-  // row-owner decomposition (gemm_lnrow_sm100.cu): 2 = always, 3 = only for K <= 1024
-  if (tuning(MMR_TUNE_GEMM_LN) == 2 || (tuning(MMR_TUNE_GEMM_LN) == 3 && K <= 1024))
+  // row-owner decomposition (gemm_lnrow_sm100.cu): 2 = always, 3 = only for K <= 1024 (one weight matrix only)
+  if (!two && (tuning(MMR_TUNE_GEMM_LN) == 2 || (tuning(MMR_TUNE_GEMM_LN) == 3 && K <= 1024)))
     return gemm_lnrow(A16, lda, W16, ldw, M, K, bias, residual, ldr, gamma, beta, eps, out16, ldo16, out32, ldo32, dtype,
                       stream);
   MMR_TRY(gemm_ln_reserve(M));
   int dev = 0;
   MMR_CUDA_OK(cudaGetDevice(&dev));
   const int ek = dtype == MMR_DT_BF16 ? 1 : 0;
-  CUtensorMap ta, tw, tr, to32, to16;
+  CUtensorMap ta, tw, tw2, tr, to32, to16;
   MMR_TRY(make_tmap_2d(&ta, A16, M, K, lda, kCtaRows, dtype));
   MMR_TRY(make_tmap_2d(&tw, W16, kLnN, K, ldw, kBN / 2, dtype));
+  MMR_TRY(make_tmap_2d(&tw2, two ? W16b : W16, kLnN, K, ldw, kBN / 2, dtype));
   MMR_TRY(make_tmap_ex(&tr, residual, M, kLnN, ldr, 2, 32, 32, 128));
   MMR_TRY(make_tmap_ex(&to32, out32, M, kLnN, ldo32, 2, 32, 32, 128));
   MMR_TRY(make_tmap_ex(&to16, out16, M, kLnN, ldo16, ek, 32, 32, 64));
   const LnWorkspace& ws = g_ln_ws[dev];
-  GemmLnParams p{M, K, bias, gamma, beta, eps, ws.stats, ws.epoch, uint32_t(dtype), g_ln_trace};
-  if (dtype == MMR_DT_BF16) return launch_ln<BF16>(ta, tw, tr, to32, to16, p, stream);
-  return launch_ln<FP16>(ta, tw, tr, to32, to16, p, stream);
+  GemmLnParams p{M, K, bias, gamma, beta, two ? biasb : bias, two ? gammab : gamma, two ? betab : beta,
+                 two ? split_row / kPairRows : 0x7fffffff, eps, ws.stats, ws.epoch, uint32_t(dtype), g_ln_trace};
+  if (dtype == MMR_DT_BF16) return launch_ln<BF16>(ta, tw, tw2, tr, to32, to16, p, stream);
+  return launch_ln<FP16>(ta, tw, tw2, tr, to32, to16, p, stream);
+}
+mmr_status gemm_ln(const void* A16, int64_t lda, const void* W16, int64_t ldw, int M, int K, const float* bias,
+                   const float* residual, int64_t ldr, const float* gamma, const float* beta, float eps, void* out16,
+                   int64_t ldo16, float* out32, int64_t ldo32, int dtype, cudaStream_t stream) {
+  return gemm_ln_2w(A16, lda, W16, nullptr, ldw, M, K, bias, nullptr, residual, ldr, gamma, nullptr, beta, nullptr, 0, eps,
+                    out16, ldo16, out32, ldo32, dtype, stream);
 }
 
 }  // namespace mmr

@@ -31,6 +31,11 @@ mmr_status gemm_ln(const void* A16, int64_t lda, const void* W16, int64_t ldw, i
                    const float* residual, int64_t ldr, const float* gamma, const float* beta, float eps, void* out16,
                    int64_t ldo16, float* out32, int64_t ldo32, int dtype, cudaStream_t stream);
 
+// the same with a second weight / bias / gamma / beta set for the rows from split_row on (a multiple of 256)
+mmr_status gemm_ln_2w(const void* A16, int64_t lda, const void* W16, const void* W16b, int64_t ldw, int M, int K,
+                      const float* bias, const float* biasb, const float* residual, int64_t ldr, const float* gamma,
+                      const float* gammab, const float* beta, const float* betab, int split_row, float eps, void* out16,
+                      int64_t ldo16, float* out32, int64_t ldo32, int dtype, cudaStream_t stream);
 // same contract, one CTA pair per 256-row block and all 768 columns (gemm_lnrow_sm100.cu); reached through gemm_ln()
 mmr_status gemm_lnrow(const void* A16, int64_t lda, const void* W16, int64_t ldw, int M, int K, const float* bias,
                       const float* residual, int64_t ldr, const float* gamma, const float* beta, float eps, void* out16,

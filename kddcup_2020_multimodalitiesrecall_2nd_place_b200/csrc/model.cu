@@ -15,10 +15,12 @@
 #include <cmath>
 #include <cstring>
 #include <map>
+#include <algorithm>
 #include <string>
 #include <vector>
 
 #include "common.cuh"
+#include "gemm_common.cuh"
 #include "kernels.cuh"
 
 namespace mmr {
@@ -570,6 +572,34 @@ struct Ctx {
     MMR_TRY(G(A, lda, W, rows, x32(row0), nullptr, 0, x32(row0), MMR_ACT_NONE));
     return LN(x32(row0), ln, rows, x16(row0), x32(row0), 1.0f, 0);
   }
+  // Two streams that share the activation buffers but not the weights (LXMERT: language rows [0, split), visual rows
+  // [split, M)) run a projection as ONE launch when the split is a multiple of the 256-row tile: full waves instead
+  // of two launches of 32 and 36 row blocks (the fused GEMM+LN kernel loses a third of its SMs at 32 blocks).
+  bool mergeable(const Linear& W1, const Linear& W2, int split) const {
+    return tuning(MMR_TUNE_LX_MERGE) != 0 && W1.n == W2.n && W1.k == W2.k && split > 0 && split % 256 == 0;
+  }
+  mmr_status G2(const void* A, int64_t lda, const Linear& W1, const Linear& W2, int M, int split, void* out16,
+                int64_t ldo16, int act) {
+    if (mergeable(W1, W2, split) && tuning(MMR_TUNE_GEMM_PAIR) != 0 &&
+        gemm_pair16_eligible(M, W1.n, W1.k, nullptr, out16, nullptr)) {
+      MMR_TRY(gemm_pair16_2w(A, lda, W1.w16, W2.w16, W1.k, M, W1.n, W1.k, W1.bias, W2.bias, split, out16, ldo16, act, dt,
+                             st));
+      return mark(K_GEMM, 2.0 * M * W1.n * W1.k);
+    }
+    MMR_TRY(G(A, lda, W1, split, nullptr, out16, ldo16, nullptr, act));
+    return G(static_cast<const uint8_t*>(A) + int64_t(split) * lda * 2, lda, W2, M - split, nullptr,
+             static_cast<uint8_t*>(out16) + int64_t(split) * ldo16 * 2, ldo16, nullptr, act);
+  }
+  mmr_status G_LN2(const void* A, int64_t lda, const Linear& W1, const Linear& W2, const LNp& ln1, const LNp& ln2,
+                   int rows, int split) {
+    if (mergeable(W1, W2, split) && gemm_ln_eligible(rows, W1.n, W1.k, dt)) {
+      MMR_TRY(gemm_ln_2w(A, lda, W1.w16, W2.w16, W1.k, rows, W1.k, W1.bias, W2.bias, x32(0), H, ln1.gamma, ln2.gamma,
+                         ln1.beta, ln2.beta, split, 1e-12f, x16(0), H, x32(0), H, dt, st));
+      return mark(K_GEMM, 2.0 * rows * W1.n * W1.k);
+    }
+    MMR_TRY(G_LN(A, lda, W1, ln1, 0, split));
+    return G_LN(static_cast<const uint8_t*>(A) + int64_t(split) * lda * 2, lda, W2, ln2, split, rows - split);
+  }
   mmr_status LN(float* x, const LNp& p, int rows, void* out16, float* out32, float scale, int accumulate) {
     MMR_TRY(layernorm(x, H, p.gamma, p.beta, 1e-12f, rows, H, out16, H, out32, H, scale, accumulate, dt, st));
     return mark(K_LAYERNORM, 0.0);
@@ -604,6 +634,21 @@ static mmr_status self_att_block(Ctx& c, const AttBlock& A, int64_t row0, int B,
 static mmr_status bert_layer(Ctx& c, const Layer& L, int64_t row0, int B, int S, const int32_t* key_mask) {
   MMR_TRY(self_att_block(c, L.att, row0, B, S, key_mask));
   return ffn_block(c, L.ffn, row0, B * S);
+}
+
+// One self-attention + FFN layer of BOTH LXMERT streams (language rows [0, nl), visual rows [nl, nl + nv)): the four
+// projections as merged launches, attention per stream.
+static mmr_status two_stream_att(Ctx& c, const AttBlock& A1, const AttBlock& A2, int B, int Lq, int R,
+                                 const int32_t* mask1, const int32_t* mask2) {
+  const int nl = B * Lq, nv = B * R;
+  MMR_TRY(c.G2(c.x16(0), c.H, A1.qkv, A2.qkv, nl + nv, nl, c.qkv(0, 0), 3 * c.H, MMR_ACT_NONE));
+  MMR_TRY(attend(c, 0, Lq, 0, Lq, mask1, B));
+  MMR_TRY(attend(c, nl, R, nl, R, mask2, B));
+  return c.G_LN2(c.ctx(0), c.H, A1.out, A2.out, A1.ln, A2.ln, nl + nv, nl);
+}
+static mmr_status two_stream_ffn(Ctx& c, const FfnBlock& F1, const FfnBlock& F2, int nl, int nv) {
+  MMR_TRY(c.G2(c.x16(0), c.H, F1.in, F2.in, nl + nv, nl, c.h->h16, F1.in.n, c.h->act));
+  return c.G_LN2(c.h->h16, F1.in.n, F1.out, F2.out, F1.ln, F2.ln, nl + nv, nl);
 }
 
 // first token of every pair: rows b*S of x16 (row stride S*H), pixelbert.py:258-266 / modeling.py:596-608
@@ -707,18 +752,31 @@ static mmr_status forward_lxmert(Ctx& c, const mmr_inputs* in, int B, float* pro
   MMR_TRY(c.LN(h->tmp32, h->label_ln, nv, c.x16(v0), c.x32(v0), third, 1));
   if (h->keep_taps)
     MMR_CUDA_OK(cudaMemcpyAsync(h->emb_tap, h->x32, size_t(nl + nv) * H * 4, cudaMemcpyDeviceToDevice, c.st));
-  for (const Layer& L : h->layers) MMR_TRY(bert_layer(c, L, 0, B, Lq, in->query_mask));       // modeling.py:577-578
-  for (const Layer& L : h->r_layers) MMR_TRY(bert_layer(c, L, v0, B, R, in->visn_mask));      // :582-583
+  // language layers (modeling.py:577-578) and visual layers (:582-583) are independent chains: the first
+  // min(9, 5) of each run pairwise through merged launches, the rest alone
+  const bool merge = tuning(MMR_TUNE_LX_MERGE) != 0 && nl % 256 == 0;
+  const size_t n_both = merge ? std::min(h->layers.size(), h->r_layers.size()) : 0;
+  for (size_t i = 0; i < n_both; ++i) {
+    MMR_TRY(two_stream_att(c, h->layers[i].att, h->r_layers[i].att, B, Lq, R, in->query_mask, in->visn_mask));
+    MMR_TRY(two_stream_ffn(c, h->layers[i].ffn, h->r_layers[i].ffn, nl, nv));
+  }
+  for (size_t i = n_both; i < h->layers.size(); ++i) MMR_TRY(bert_layer(c, h->layers[i], 0, B, Lq, in->query_mask));
+  for (size_t i = n_both; i < h->r_layers.size(); ++i) MMR_TRY(bert_layer(c, h->r_layers[i], v0, B, R, in->visn_mask));
   for (const XLayer& X : h->x_layers) {                                                       // :589-591
     // cross attention both ways with ONE weight set, both from the pre-update streams (modeling.py:462-463)
     MMR_TRY(qkv_proj(c, X.cross.qkv, 0, nl + nv));
     MMR_TRY(attend(c, 0, Lq, v0, R, in->visn_mask, B));
     MMR_TRY(attend(c, v0, R, 0, Lq, in->query_mask, B));
     MMR_TRY(out_proj_ln(c, X.cross, 0, nl + nv));
-    MMR_TRY(self_att_block(c, X.lang_self, 0, B, Lq, in->query_mask));
-    MMR_TRY(self_att_block(c, X.visn_self, v0, B, R, in->visn_mask));
-    MMR_TRY(ffn_block(c, X.lang_ffn, 0, nl));
-    MMR_TRY(ffn_block(c, X.visn_ffn, v0, nv));
+    if (merge) {
+      MMR_TRY(two_stream_att(c, X.lang_self, X.visn_self, B, Lq, R, in->query_mask, in->visn_mask));
+      MMR_TRY(two_stream_ffn(c, X.lang_ffn, X.visn_ffn, nl, nv));
+    } else {
+      MMR_TRY(self_att_block(c, X.lang_self, 0, B, Lq, in->query_mask));
+      MMR_TRY(self_att_block(c, X.visn_self, v0, B, R, in->visn_mask));
+      MMR_TRY(ffn_block(c, X.lang_ffn, 0, nl));
+      MMR_TRY(ffn_block(c, X.visn_ffn, v0, nv));
+    }
   }
   MMR_TRY(pooler(c, B, Lq));
   // logit_fc: Linear(768,1536) -> erf-GELU -> LayerNorm(1536) -> Linear(1536,2)  (kdd_model.py:167-172)

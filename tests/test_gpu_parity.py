@@ -292,3 +292,32 @@ def test_zk_label_term_once_per_phrase_is_bit_identical(phrases):
     finally:
         _lib.check(lib.mmr_set_tuning(_lib.TUNE_LABEL_DEDUP, 1))
         sc.close()
+
+
+@pytest.mark.parametrize("B,lq", [(8, 32), (16, 16), (12, 20)])
+def test_lxmert_two_stream_merged_launches(B, lq):
+    """LXMERT's language and visual streams share the activation buffers but not the weights; when batch x query
+    length is a multiple of the 256-row tile their projections run as ONE launch each (two weight matrices over a
+    row split).  Same bits as the per-stream launches, within tolerance of the oracle; B x lq = 240 exercises the
+    fall-back (split not tile-aligned).  Unequal layer counts: 3 language / 2 visual layers pair up twice."""
+    from kddcup_2020_multimodalitiesrecall_2nd_place_b200 import _lib
+    lib = _lib.load()
+    cfg = ModelConfig(LXMERT, n_layers=3, n_r_layers=2, n_x_layers=2, lq=lq, nbox=36, vocab=2000)
+    w = synth.make_weights(cfg, seed=synth.SEED0 + 11)
+    inp = synth.make_inputs(cfg, B, seed=synth.SEED0 + 11, n_queries=2)
+    sc = _scorer(cfg, w, B)
+    try:
+        out, launches = {}, {}
+        for merged in (1, 0):
+            _lib.check(lib.mmr_set_tuning(_lib.TUNE_LX_MERGE, merged))
+            out[merged], _ = _gpu_probs(sc, inp)
+            launches[merged] = sc.launches_per_forward()
+        assert torch.equal(out[0], out[1])
+        if (B * lq) % 256 == 0:
+            assert launches[1] < launches[0]
+        else:
+            assert launches[1] == launches[0]
+        assert (out[1] - _oracle(cfg, w, inp)["probs"]).abs().max().item() <= TOL
+    finally:
+        _lib.check(lib.mmr_set_tuning(_lib.TUNE_LX_MERGE, 1))
+        sc.close()
