@@ -51,6 +51,10 @@ struct T2Roles {
   static constexpr int kProducerWarp = WPG == 3 ? 7 : 17;
   static constexpr int kMmaWarp = WPG == 3 ? 11 : 18;     // issues S = Q K^T; owns the TMEM allocation
   static constexpr int kPvWarp = WPG == 3 ? 15 : 19;      // issues O = P V
+  // O rows leave through a per-warp 4 KB shared-memory stage as 128-byte coalesced rows (4 rows per store
+  // instruction instead of 32 different lines); the 4-warps-per-group kernel (lds, S = 104) needs the shared
+  // memory for its operand ring and stores straight from registers
+  static constexpr uint32_t kOutStageBytes = WPG == 3 ? 12 * 4096 : 0;
   __device__ static bool is_softmax(int warp) { return WPG == 3 ? (warp & 3) != 3 : warp < 16; }
 };
 constexpr uint32_t kT2QReadBytes = 128 * 128;      // what the 128-row UMMA reads from an item's Q base
@@ -106,7 +110,8 @@ struct T2Layout {
   int n_stages;
   size_t smem_bytes;
 };
-__host__ __device__ inline T2Layout t2_layout(int Sq, int Sk) {
+// out_stage_bytes: per-CTA staging for the coalesced output path (12 warps x 4 KB in the 3-warps-per-group kernels)
+__host__ __device__ inline T2Layout t2_layout(int Sq, int Sk, uint32_t out_stage_bytes) {
   T2Layout L;
   const int SkP = (Sk + 15) & ~15, Sq8 = (Sq + 7) & ~7;
   L.q_bytes = uint32_t(Sq8) * 128u;
@@ -114,7 +119,7 @@ __host__ __device__ inline T2Layout t2_layout(int Sq, int Sk) {
   L.stage_bytes = L.q_bytes + 2u * L.kv_bytes;
   // the last stage's Q read (128 rows) must stay inside the allocation
   L.pad_bytes = L.stage_bytes >= kT2QReadBytes ? 0u : kT2QReadBytes - L.stage_bytes;
-  const size_t fixed = 1024 + L.pad_bytes + size_t(kT2MaxStages) * 512 + 4 * 512 + 512;
+  const size_t fixed = 1024 + L.pad_bytes + size_t(kT2MaxStages) * 512 + 4 * 512 + 512 + out_stage_bytes;
   int n = int((size_t(227) * 1024 - fixed) / L.stage_bytes);
   L.n_stages = n > kT2MaxStages ? kT2MaxStages : n;
   L.smem_bytes = fixed + size_t(L.n_stages) * L.stage_bytes;
@@ -136,16 +141,17 @@ __global__ void __launch_bounds__(T2Roles<WPG>::kThreads, 1)
 attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const int32_t* __restrict__ key_mask,
                      typename E16::T* __restrict__ out, int64_t ldo, int Sq, int Sk, int heads, int n_items,
-                     uint32_t idesc_fmt, unsigned long long* trace) {
+                     uint32_t idesc_fmt, unsigned long long* trace, int ablate) {
   using T = typename E16::T;
   extern __shared__ __align__(1024) uint8_t smem_t2[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_t2) + 1023) & ~uintptr_t(1023));
-  const T2Layout L = t2_layout(Sq, Sk);
+  const T2Layout L = t2_layout(Sq, Sk, T2Roles<WPG>::kOutStageBytes);
   const int SkP = (Sk + 15) & ~15;
   const int n_stages = L.n_stages;
   float* mask_s = reinterpret_cast<float*>(ring + size_t(n_stages) * L.stage_bytes + L.pad_bytes);   // [stages][128]
   int32_t* raw_s = reinterpret_cast<int32_t*>(mask_s + kT2MaxStages * 128);                          // [4][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(raw_s + 4 * 128);
+  uint8_t* out_stage = reinterpret_cast<uint8_t*>(raw_s + 4 * 128);                                  // [12][4 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + T2Roles<WPG>::kOutStageBytes);
   uint64_t* full_bar = bars;                          // [6] TMA -> MMA / softmax (mask row)
   uint64_t* empty_bar = bars + kT2MaxStages;          // [6] PV retired -> producer
   uint64_t* s_ready = bars + 2 * kT2MaxStages;        // [4] S complete in TMEM
@@ -208,10 +214,15 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const int b = item / heads, h = item - b * heads;
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         uint8_t* st = ring + size_t(stage) * L.stage_bytes;
+        if (ablate & 8) {
+          mbar_arrive_expect_tx(&full_bar[stage], uint32_t(Sq) * 128u);
+          tma_load_2d(st, &tmap_q, &full_bar[stage], h * kT2HeadDim, b * Sq);
+        } else {
         mbar_arrive_expect_tx(&full_bar[stage], uint32_t(Sq + 2 * Sk) * 128u);
         tma_load_2d(st, &tmap_q, &full_bar[stage], h * kT2HeadDim, b * Sq);
         tma_load_2d(st + L.q_bytes, &tmap_k, &full_bar[stage], h * kT2HeadDim, b * Sk);
         tma_load_2d(st + L.q_bytes + L.kv_bytes, &tmap_v, &full_bar[stage], h * kT2HeadDim, b * Sk);
+        }
         MMR_T2_STAMP(n, 0);
         if (++stage == n_stages) {
           stage = 0;
@@ -225,7 +236,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     // A key_mask load is an L2 round trip (~1 us): the raw int32 rows travel global -> shared with cp.async THREE
     // ITEMS AHEAD into a 4-entry staging ring (each lane reads back only what it fetched itself).
     auto issue_mask = [&](int n) {
-      if (n < my_items && key_mask != nullptr) {
+      if (n < my_items && key_mask != nullptr && !(ablate & 2)) {
         const int b = (int(blockIdx.x) + n * int(gridDim.x)) / heads;
         int32_t* dst = raw_s + (n & 3) * 128;
         for (int i = lane; i < Sk; i += 32) cp_async_4(dst + i, key_mask + int64_t(b) * Sk + i);
@@ -274,7 +285,8 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const uint32_t tmem_s = tmem_base + uint32_t(slot * kT2SlotCols);
 #pragma unroll
         for (int k = 0; k < kT2HeadDim / kUmmaK; ++k)
-          umma_f16(tmem_s, q_desc + uint64_t(2 * k), k_desc + uint64_t(2 * k), idesc_s, k != 0 ? 1u : 0u);
+          if (k == 0 || !(ablate & 32))
+            umma_f16(tmem_s, q_desc + uint64_t(2 * k), k_desc + uint64_t(2 * k), idesc_s, k != 0 ? 1u : 0u);
         umma_commit(&s_ready[slot]);
         MMR_T2_STAMP(n, 1);
         if (++stage == n_stages) {
@@ -299,7 +311,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const uint32_t st = smem_u32(ring + size_t(stage) * L.stage_bytes);
         const uint64_t v_desc = umma_desc_k_sw128(st + L.q_bytes + L.kv_bytes);
         const uint32_t tmem_p = tmem_base + uint32_t(slot * kT2SlotCols), tmem_o = tmem_p + 64u;
-        for (int ks = 0; ks < SkP / kUmmaK; ++ks)
+        for (int ks = 0; ks < ((ablate & 32) ? 1 : SkP / kUmmaK); ++ks)
           umma_f16_ts(tmem_o, tmem_p + uint32_t(8 * ks), v_desc + uint64_t(128 * ks), idesc_o, ks != 0 ? 1u : 0u);
         MMR_T2_STAMP(n, 10);
         umma_commit(&o_ready[slot]);
@@ -328,7 +340,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       tc_fence_after();
       if (w == 0 && lane == 0) MMR_T2_STAMP(n, 3);
       float inv = 0.f;
-      if (live) {
+      if (live && !(ablate & 4)) {
         // t = S / 8 + mask in the log2 domain; p = 2^(t - max); P as packed 16-bit pairs over the first SkP / 2
         // columns of S (columns [8c, 8c + 8) were read, as S columns, by this very thread before it overwrites them)
         const float4* m4 = reinterpret_cast<const float4*>(sMask);
@@ -423,7 +435,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       mbar_wait(&o_ready[g], use & 1u);
       tc_fence_after();
       if (w == 0 && lane == 0) MMR_T2_STAMP(n, 5);
-      if (live) {
+      if (live && !(ablate & 16)) {
         uint32_t o0[32], o1[32];
         tmem_ld_32x32(tmem_o, o0);
         tmem_ld_32x32(tmem_o + 32u, o1);
@@ -431,7 +443,33 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&slot_free[g]);
-        if (row < Sq) {
+        if constexpr (WPG == 3) {
+          // this thread's row -> the warp's stage (16-byte units XOR-swizzled by the row: conflict-free both ways),
+          // then row-major read-back: every store instruction covers four whole 128-byte row segments
+          uint8_t* stg = out_stage + size_t(g * 3 + w) * 4096;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((uint32_t(u) ^ uint32_t(lane & 7)) << 4)) = make_uint4(
+                E16::pack(__uint_as_float(o0[8 * u]) * inv, __uint_as_float(o0[8 * u + 1]) * inv),
+                E16::pack(__uint_as_float(o0[8 * u + 2]) * inv, __uint_as_float(o0[8 * u + 3]) * inv),
+                E16::pack(__uint_as_float(o0[8 * u + 4]) * inv, __uint_as_float(o0[8 * u + 5]) * inv),
+                E16::pack(__uint_as_float(o0[8 * u + 6]) * inv, __uint_as_float(o0[8 * u + 7]) * inv));
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((uint32_t(4 + u) ^ uint32_t(lane & 7)) << 4)) = make_uint4(
+                E16::pack(__uint_as_float(o1[8 * u]) * inv, __uint_as_float(o1[8 * u + 1]) * inv),
+                E16::pack(__uint_as_float(o1[8 * u + 2]) * inv, __uint_as_float(o1[8 * u + 3]) * inv),
+                E16::pack(__uint_as_float(o1[8 * u + 4]) * inv, __uint_as_float(o1[8 * u + 5]) * inv),
+                E16::pack(__uint_as_float(o1[8 * u + 6]) * inv, __uint_as_float(o1[8 * u + 7]) * inv));
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rl = i * 4 + (lane >> 3), u = lane & 7;
+            const uint4 val = *reinterpret_cast<const uint4*>(stg + rl * 128 + ((uint32_t(u) ^ uint32_t(rl & 7)) << 4));
+            const int r = w * 32 + rl;
+            if (r < Sq && !(ablate & 1)) *reinterpret_cast<uint4*>(out + (int64_t(b) * Sq + r) * ldo + h * kT2HeadDim + u * 8) = val;
+          }
+          __syncwarp();   // the stage is rewritten by this warp's next item
+        } else if (row < Sq) {
           uint4* orow = reinterpret_cast<uint4*>(out + (int64_t(b) * Sq + row) * ldo + h * kT2HeadDim);
 #pragma unroll
           for (int u = 0; u < 4; ++u)
@@ -464,6 +502,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 }
 
 static unsigned long long* g_t2_trace = nullptr;
+static int g_t2_ablate = 0;   // timing experiments only (tools/attn_ablate.py): results are wrong when non-zero
 
 template <class E16, int NCH, int WPG>
 static mmr_status launch_attention_tc2(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
@@ -481,12 +520,12 @@ static mmr_status launch_attention_tc2(const void* q, int64_t ldq, const void* k
   MMR_TRY(make_tmap_ex(&tq, q, int64_t(B) * Sq, int64_t(heads) * kT2HeadDim, ldq, ek, kT2HeadDim, Sq, 128));
   MMR_TRY(make_tmap_ex(&tk, k, int64_t(B) * Sk, int64_t(heads) * kT2HeadDim, ldk, ek, kT2HeadDim, Sk, 128));
   MMR_TRY(make_tmap_ex(&tv, v, int64_t(B) * Sk, int64_t(heads) * kT2HeadDim, ldv, ek, kT2HeadDim, Sk, 128));
-  const T2Layout L = t2_layout(Sq, Sk);
+  const T2Layout L = t2_layout(Sq, Sk, T2Roles<WPG>::kOutStageBytes);
   MMR_REQUIRE(L.n_stages >= 2, "attention_tc2: operand ring does not fit (Sq=%d Sk=%d)", Sq, Sk);
   const int n_items = B * heads;
   const int grid = std::min(n_items, sm_count());   // one CTA per SM: it allocates all 512 TMEM columns
   MMR_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(T2Roles<WPG>::kThreads), L.smem_bytes, stream, tq, tk, tv, key_mask,
-                         static_cast<T*>(out), ldo, Sq, Sk, heads, n_items, uint32_t(dtype), g_t2_trace));
+                         static_cast<T*>(out), ldo, Sq, Sk, heads, n_items, uint32_t(dtype), g_t2_trace, g_t2_ablate));
   return MMR_OK;
 }
 template <class E16>
@@ -521,3 +560,4 @@ mmr_status attention_tc2(const void* q, int64_t ldq, const void* k, int64_t ldk,
 
 /* Debug only (not in the public header): device buffer of [grid][24 items][16] uint64 stamps, or null. */
 extern "C" void mmr_debug_set_attn_trace(unsigned long long* dev_buf) { mmr::g_t2_trace = dev_buf; }
+extern "C" void mmr_debug_set_attn_ablate(int bits) { mmr::g_t2_ablate = bits; }
