@@ -208,11 +208,13 @@ def main():
         sc.forward_device(dev_sets[i % n_sets], probs_out=scores[i % K])
     if world > 1:
         dist.all_gather_into_tensor(gathered.view(-1), scores[:, :, 1].contiguous().view(-1))
-    barrier()
+    # NVML initialisation takes ~15 ms: before the barrier, or rank 0 would enter the timed region that much after
+    # the other ranks and they would wait for it in the all-gather
     sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
     if sampler:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for k in range(K):
         sc.forward_device(dev_sets[k % n_sets], probs_out=scores[k])
