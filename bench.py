@@ -97,7 +97,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.05)   # (a denser poll competes with the launch loop for the interpreter lock)
 
     def start(self):
         if self.nv is not None:
