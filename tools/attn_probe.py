@@ -1,5 +1,7 @@
 """Attention kernels side by side: correctness of the selected variant on the test shapes, launch time of every
-variant at the bench shapes (CUDA events, rotating qkv buffers larger than L2 together)."""
+variant at the bench shapes (CUDA events, rotating qkv buffers larger than L2 together).  One Python call per launch
+costs ~20 us of host time (tensor maps, ctypes): below that the numbers are host-bound — tools/attn_ablate.py replays
+the launches from a CUDA graph for GPU-bound times."""
 import os
 import sys
 
