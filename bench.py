@@ -61,8 +61,8 @@ def workload_name(cfg, batch):
 
 
 # ---------------------------------------------------------------------------------------------- clocks
-class ClockSampler:
-    """Samples SM clock / power / throttle reasons of one GPU through NVML while the timed region runs."""
+class NvmlThreadSampler:
+    """Fallback: samples SM clock / throttle reasons of one GPU through NVML from a thread of THIS process."""
 
     def __init__(self, index):
         self.samples, self.reasons = [], set()
@@ -97,7 +97,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.05)   # (a denser poll competes with the launch loop for the interpreter lock)
+            self._stop.wait(0.05)
 
     def start(self):
         if self.nv is not None:
@@ -111,7 +111,88 @@ class ClockSampler:
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "reasons": sorted(self.reasons), "samples": len(self.samples), "source": "nvml thread"}
+
+
+class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region, sampled by a separate `nvidia-smi -lms` process (the
+    profiling recipe's clocks line).  An NVML poll from a thread of the benchmarking process itself measured ~1 %
+    slower steps on the rank that ran it (rank 0 was the slowest rank of every multi-GPU run); the subprocess is
+    started before the barrier and only its samples stamped inside [start(), stop()] are used.  Falls back to the
+    in-process NVML thread when nvidia-smi is not usable."""
+
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+    REASONS = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+
+    def __init__(self, index):
+        import shutil
+        import subprocess
+        import tempfile
+        self.proc, self.fallback = None, None
+        self.t0 = self.t1 = None
+        exe = shutil.which("nvidia-smi")
+        if exe is not None and os.environ.get("MMR_BENCH_SAMPLER", "smi") == "smi":
+            self.log = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            try:
+                self.proc = subprocess.Popen([exe, "-i", str(index), f"--query-gpu={self.FIELDS}",
+                                              "--format=csv,noheader,nounits", "-lms", "50"],
+                                             stdout=self.log, stderr=subprocess.DEVNULL)
+            except Exception:  # pragma: no cover
+                self.proc = None
+            if self.proc is not None:
+                import atexit
+                atexit.register(lambda p=self.proc: p.poll() is None and p.kill())
+        if self.proc is None:
+            self.fallback = NvmlThreadSampler(index)
+
+    def start(self):
+        self.t0 = time.time()
+        if self.fallback is not None:
+            self.fallback.start()
+
+    def _parse(self):
+        import datetime
+        mhz, reasons, max_mhz = [], set(), None
+        self.log.flush()
+        with open(self.log.name) as f:
+            for line in f:
+                c = [x.strip() for x in line.split(",")]
+                if len(c) != 7:
+                    continue
+                try:
+                    ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    clk = float(c[1])
+                    max_mhz = float(c[2])
+                except ValueError:
+                    continue
+                if self.t0 - 0.025 <= ts <= self.t1 + 0.025:
+                    mhz.append(clk)
+                    for name, v in zip(self.REASONS, c[3:]):
+                        if v == "Active":
+                            reasons.add(name)
+        return mhz, reasons, max_mhz
+
+    def stop(self):
+        self.t1 = time.time()
+        if self.fallback is not None:
+            return self.fallback.stop()
+        time.sleep(0.06)   # let the sample that covers the end of the region land in the file
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # pragma: no cover
+            self.proc.kill()
+        mhz, reasons, max_mhz = self._parse()
+        try:
+            os.unlink(self.log.name)
+        except OSError:
+            pass
+        if not mhz:
+            return {"sm_mhz": None, "sm_max_mhz": max_mhz, "reasons": [], "samples": 0, "source": "nvidia-smi (no samples)"}
+        return {"sm_mhz": float(np.median(mhz)), "sm_max_mhz": int(max_mhz), "reasons": sorted(reasons),
+                "samples": len(mhz), "source": "nvidia-smi -lms 50 subprocess"}
 
 
 # ---------------------------------------------------------------------------------------------- CPU arm
