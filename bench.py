@@ -116,10 +116,10 @@ class NvmlThreadSampler:
 
 class ClockSampler:
     """SM clock and throttle reasons DURING the timed region, sampled by a separate `nvidia-smi -lms` process (the
-    profiling recipe's clocks line).  An NVML poll from a thread of the benchmarking process itself measured ~1 %
-    slower steps on the rank that ran it (rank 0 was the slowest rank of every multi-GPU run); the subprocess is
-    started before the barrier and only its samples stamped inside [start(), stop()] are used.  Falls back to the
-    in-process NVML thread when nvidia-smi is not usable."""
+    profiling recipe's clocks line): it keeps NVML calls out of the process that launches the kernels.  (An A/B at
+    N = 1 measured no difference between this and an in-process NVML thread: 69.2 vs 69.1 k pairs/s.)  The
+    subprocess is started before the barrier and only its samples stamped inside [start(), stop()] are used.  Falls
+    back to the in-process NVML thread when nvidia-smi is not usable."""
 
     FIELDS = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
