@@ -64,12 +64,13 @@ int mmr_abi_version(void);
  *   MMR_TUNE_GEMM_LN       (env MMR_GEMM_LN,      default 1) fused projection + residual + LayerNorm kernel: 1 = three
  *                                                            CTA pairs per 256-row block meeting through a global table
  *                                                            (gemm_ln_sm100.cu), 2 = one pair owns the block and all 768
- *                                                            columns (gemm_lnrow_sm100.cu), 0 = GEMM + LayerNorm kernels
+ *                                                            columns (gemm_lnrow_sm100.cu; 3 = that one only for K <= 1024),
+ *                                                            0 = GEMM + LayerNorm kernels
  *   MMR_TUNE_PDL           (env MMR_PDL,          default 1) programmatic dependent launch between the kernels
  *   MMR_TUNE_ATTN_TMA      (env MMR_ATTN_TMA,     default 0) persistent TMA-pipelined mma.sync attention kernel
  *                                                            (measured slower than one CTA per (pair, head): 40 vs 32 us)
  *   MMR_TUNE_ATTN_TC       (env MMR_ATTN_TC,      default 2) tcgen05 / TMEM attention: 2 = pipelined four items deep per
- *                                                            SM with P kept in TMEM (attention_tc2.cu: 25.5 us at B=256,
+ *                                                            SM with P kept in TMEM (attention_tc2.cu: 24-25 us at B=256,
  *                                                            S=68 against 31.7 us for the mma.sync kernel), 1 = first
  *                                                            version, one item in flight per CTA (attention_tc.cu, 40 us),
  *                                                            0 = mma.sync kernels
