@@ -10,7 +10,11 @@ Pinning status
     the nDCG known answer 0.7098 (kdd-report-final.pdf table 5) reproduced from shipped score files.
   * LXMERT: pinned against the reference's OWN PyTorch code, imported from /root/reference in the dev container
     (oracle/lxmert_ref.py); golden vectors generated from it are committed under tests/golden/ with the script.
-  * ImageBert zk / lds: TF-1.12 + Python 2 are not installable, and the reference ships no activations or weights:
-    PARITY UNPINNED for these two encoders beyond what they share with the pinned LXMERT blocks (attention,
-    post-LN block, LayerNorm, GELU, pooler).  The restatement follows SURVEY.md appendix A line by line.
+  * ImageBert zk / lds: TF-1.12 + Python 2 are not installable, and the reference ships no activations or weights.
+    Pinned at the level of the model code: the reference's OWN graph-building code (imagebert_zk/pixelbert.py +
+    model_triple.py, imagebert_lds/src/pixelmodel.py + get_next_sentence_output) runs unmodified on tools/tf1_shim.py,
+    an eager stand-in for the TensorFlow ops it calls, and its outputs on seeded synthetic weights / inputs are
+    committed as tests/golden/{zk,lds}_ref_shim_*.npz (tools/make_golden.py --tf-shim; re-derived from
+    /root/reference on every CPU test run in the dev container).  PARITY UNPINNED only below that: the arithmetic of
+    the individual TensorFlow ops is restated in the shim from the TF 1.12 documentation.
 """

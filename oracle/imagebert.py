@@ -1,7 +1,15 @@
 """fp32 CPU restatement of the two TF-1 ImageBert scorers.  TEST INFRASTRUCTURE (see oracle/__init__.py).
 
-PARITY UNPINNED: TensorFlow 1.12 / Python 2 cannot run here and the reference ships neither weights nor
-activations for these graphs; this file follows the reference source line by line instead.
+Pinning: TensorFlow 1.12 / Python 2 cannot run here and the reference ships neither weights nor activations for
+these graphs.  What pins this file is the reference's OWN model code (imagebert_zk/pixelbert.py + model_triple.py,
+imagebert_lds/src/pixelmodel.py + get_next_sentence_output) executed unmodified on tools/tf1_shim.py — an eager
+stand-in for the TensorFlow ops it calls — on seeded synthetic weights / inputs: tests/golden/{zk,lds}_ref_shim_*.npz
+(tools/make_golden.py --tf-shim), compared in tests/test_oracle.py to 1e-5 on probs, pooled output and per-token
+statistics of the embedding and final layers, 2 and 12 layers, reference-initialiser and trained-like weights.  That
+pins the WIRING (ops, order, variable names, shapes, masks, constants, quirks) to the reference's source.  The
+arithmetic of the individual TensorFlow ops (conv2d SAME / default ReLU, fully_connected, dense, layer_norm eps,
+l2_normalize, dropout at inference) is restated in the shim from the TF 1.12 documentation: PARITY UNPINNED at that
+level, and only there.
 
 Weights: dict name -> fp32 tensor with the reference's TF variable names and layouts (kernels are [in, out]).
 """

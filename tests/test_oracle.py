@@ -67,6 +67,43 @@ def test_lxmert_restatement_matches_reference_code(tag):
     np.testing.assert_allclose(out["x_norm"].numpy(), g["x_norm"], atol=1e-5)
 
 
+@pytest.mark.parametrize("tag", ["small", "small_trained", "native"])
+@pytest.mark.parametrize("kind", ["zk", "lds"])
+def test_imagebert_restatement_matches_reference_code_on_tf_shim(kind, tag):
+    """oracle/imagebert.py vs outputs of the reference's own TF-1 model code (model_triple.model_attention_channel_e;
+    pixelmodel.BertModel + get_next_sentence_output) executed unmodified on the eager TensorFlow-op stand-in
+    (tools/tf1_shim.py, fixtures by tools/make_golden.py --tf-shim): probs, pooled output, per-token mean / L2 norm of
+    the embedding output and of the last encoder layer, and the exact set of variable names the reference asks for."""
+    g = np.load(os.path.join(GOLD, f"{kind}_ref_shim_{tag}.npz"))
+    cfg = ModelConfig(**ast.literal_eval(str(g["cfg"])))
+    w = synth.make_weights(cfg, seed=int(g["seed"]), trained_like=bool(g["trained_like"]))
+    assert _digest(w) == str(g["weights_sha256"]), "synthetic weight generator drifted from the golden fixture"
+    assert sorted(w) == list(g["variables"]), "the reference's variable names differ from the weight set's"
+    inp = imagebert.to_torch(synth.make_inputs(cfg, int(g["batch"]), seed=int(g["seed"])))
+    fwd = imagebert.zk_forward if kind == "zk" else imagebert.lds_forward
+    out = fwd(imagebert.to_torch(w), inp, cfg.n_layers)
+
+    def stats(x):
+        x = x.numpy()
+        return np.stack([x.mean(-1), np.sqrt((x * x).sum(-1))], -1)
+    np.testing.assert_allclose(out["probs"].numpy(), g["probs"], atol=1e-5)
+    np.testing.assert_allclose(out["pooled"].numpy(), g["pooled"], atol=1e-5)
+    np.testing.assert_allclose(stats(out["embedding_output"]), g["embedding_stats"], atol=1e-5, rtol=1e-5)
+    np.testing.assert_allclose(stats(out["sequence_output"]), g["sequence_stats"], atol=1e-5, rtol=1e-5)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/code/imagebert_zk"), reason="reference tree not mounted")
+def test_tf_shim_fixtures_reproduce_from_the_reference_tree():
+    """Dev container only: re-runs the reference's model code on the shim and compares with the committed fixtures."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "make_golden.py"), "--tf-shim", "--check"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    assert "committed fixtures reproduce" in r.stdout
+
+
 def test_zk_label_conv_same_padding_matches_conv2d():
     """Quirk 1+2: slim.conv2d [1,8] SAME = pad 3 left / 4 right, bias, ReLU, then mean."""
     cfg = ModelConfig(ZK, n_layers=1, lq=6, nbox=3, vocab=50)

@@ -6,6 +6,14 @@
   ndcg_kat.npz      shipped valid scores + valid answers (nDCG@5 known answer 0.7098, report table 5)
   lxmert_ref_*.npz  outputs of the reference's OWN LXMERT code (oracle/lxmert_ref.py) on seeded synthetic
                     weights/inputs from kddcup_2020_multimodalitiesrecall_2nd_place_b200.synth
+
+    python tools/make_golden.py --tf-shim [--check]
+
+  zk_ref_shim_*.npz, lds_ref_shim_*.npz   outputs of the reference's OWN TF-1 model code (imagebert_zk/pixelbert.py +
+                    model_triple.py; imagebert_lds/src/pixelmodel.py + get_next_sentence_output of
+                    run_pretraining_predict_score.py) executed unmodified on tools/tf1_shim.py, an eager stand-in for
+                    the TensorFlow ops it calls (TF 1.12 itself cannot be installed here).  --check regenerates in
+                    memory and compares with the committed files instead of writing them.
 """
 import hashlib
 import os
@@ -93,6 +101,130 @@ def lxmert_ref():
             probs=out["probs"].numpy(), logit=out["logit"].numpy(), x_norm=out["x_norm"].numpy())
         print("lxmert_ref", tag, out["probs"][:, 1].numpy())
 
+
+# ---------------------------------------------------------------------------------------------- TF-1 model code on the shim
+def _bert_config_json(cfg, path):
+    import json
+    json.dump({"vocab_size": cfg.vocab, "hidden_size": cfg.hidden, "num_hidden_layers": cfg.n_layers,
+               "num_attention_heads": cfg.heads, "intermediate_size": cfg.intermediate, "hidden_act": "gelu",
+               "hidden_dropout_prob": 0.1, "attention_probs_dropout_prob": 0.1, "max_position_embeddings": cfg.max_pos,
+               "type_vocab_size": cfg.type_vocab, "initializer_range": 0.02}, open(path, "w"))
+
+
+def _fresh_import(name, src_dir):
+    import importlib
+    for m in ("model_triple", "pixelbert", "pixelmodel"):
+        sys.modules.pop(m, None)
+    if src_dir in sys.path:
+        sys.path.remove(src_dir)
+    sys.path.insert(0, src_dir)
+    return importlib.import_module(name)
+
+
+def zk_on_shim(cfg, w, inp):
+    """model_triple.model_attention_channel_e (code/imagebert_zk/model_triple.py:162-214) as the reference's
+    evaluate_normal.py:222-236 feeds it, is_training=False.  The reference hard-codes 20 query tokens and 10 boxes."""
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import tf1_shim
+    tf1_shim.install(w)
+    T = tf1_shim.Tensor
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, "user_data"))
+        os.makedirs(os.path.join(d, "work"))
+        _bert_config_json(cfg, os.path.join(d, "user_data", "bert_config.json"))
+        os.chdir(os.path.join(d, "work"))          # model_triple.py:19 reads '../user_data/bert_config.json' at import
+        try:
+            mt = _fresh_import("model_triple", os.path.join(REF, "code/imagebert_zk"))
+            captured = {}
+            orig = mt.image_bert
+
+            def image_bert(*a, **k):
+                captured["model"] = orig(*a, **k)
+                return captured["model"]
+            mt.image_bert = image_bert
+            _, probs, _ = mt.model_attention_channel_e(
+                T(inp["num_boxes"]), T(inp["boxes"]), T(inp["feats"]), T(inp["label_ids"]), None, T(inp["query_ids"]),
+                T(inp["len_query"]), T(inp["labels"]), T(inp["segment_ids"]), None, None, is_training=False)
+        finally:
+            os.chdir(cwd)
+    m = captured["model"]
+    return {"probs": probs.numpy(), "pooled": m.get_pooled_output().numpy(),
+            "embedding_output": m.embedding_output.numpy(), "sequence_output": m.sequence_output.numpy(),
+            "variables": sorted(tf1_shim.used_variables())}
+
+
+def lds_on_shim(cfg, w, inp):
+    """pixelmodel.BertModel called as bertmodel() does (run_pretraining_predict_score.py:324-331) and that file's
+    get_next_sentence_output (479-501), extracted by name (importing the script would run its flag definitions)."""
+    import ast
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import tf1_shim
+    tf = tf1_shim.install(w)
+    T = tf1_shim.Tensor
+    src = os.path.join(REF, "code/imagebert_lds/src")
+    pm = _fresh_import("pixelmodel", src)
+    with tempfile.TemporaryDirectory() as d:
+        _bert_config_json(cfg, os.path.join(d, "bert_config.json"))
+        bert_config = pm.BertConfig.from_json_file(os.path.join(d, "bert_config.json"))
+    model = pm.BertModel(imgfeat=T(inp["feats"]), config=bert_config, is_training=False, input_ids=T(inp["query_ids"]),
+                         label_ids=T(inp["label_ids"]), token_type_ids=T(inp["segment_ids"]),
+                         use_one_hot_embeddings=False, random_sample=False)
+    tree = ast.parse(open(os.path.join(src, "run_pretraining_predict_score.py")).read())
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "get_next_sentence_output"][0]
+    ns = {"tf": tf, "pixelmodel": pm}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "run_pretraining_predict_score.py", "exec"), ns)
+    _, _, _, probs = ns["get_next_sentence_output"](bert_config, model.get_pooled_output(), T(inp["labels"]))
+    return {"probs": probs.numpy(), "pooled": model.get_pooled_output().numpy(),
+            "embedding_output": model.embedding_output.numpy(), "sequence_output": model.sequence_output.numpy(),
+            "variables": sorted(tf1_shim.used_variables())}
+
+
+def _token_stats(x):
+    """[B, S, H] activations -> per-token mean and L2 norm (small enough to commit)."""
+    return np.stack([x.mean(-1), np.sqrt((x * x).sum(-1))], -1).astype(np.float32)
+
+
+def tf_shim_refs(check=False):
+    import torch
+    from kddcup_2020_multimodalitiesrecall_2nd_place_b200 import synth
+    from kddcup_2020_multimodalitiesrecall_2nd_place_b200.config import LDS, ZK, ModelConfig
+    torch.set_num_threads(8)
+    cases = {"small": (2, 4, False), "small_trained": (2, 4, True), "native": (12, 3, True)}
+    worst = 0.0
+    for kind, fn in ((ZK, zk_on_shim), (LDS, lds_on_shim)):
+        for tag, (layers, B, tl) in cases.items():
+            cfg = ModelConfig(kind, n_layers=layers, lq=20, nbox=10, vocab=2000)     # the reference's native shapes
+            seed = synth.SEED0 + 5
+            w = synth.make_weights(cfg, seed=seed, trained_like=tl)
+            inp = synth.make_inputs(cfg, B, seed=seed)
+            out = fn(cfg, w, inp)
+            assert out["variables"] == sorted(w), (sorted(set(w) ^ set(out["variables"])))
+            rec = dict(cfg=np.array(str(cfg.to_dict())), batch=np.array(B), trained_like=np.array(tl), seed=np.array(seed),
+                       weights_sha256=np.array(weights_digest(w)), probs=out["probs"], pooled=out["pooled"],
+                       embedding_stats=_token_stats(out["embedding_output"]),
+                       sequence_stats=_token_stats(out["sequence_output"]), variables=np.array(out["variables"]))
+            name = kind.replace("imagebert_", "")
+            path = os.path.join(OUT, f"{name}_ref_shim_{tag}.npz")
+            if check:
+                g = np.load(path)
+                for k in ("probs", "pooled", "embedding_stats", "sequence_stats"):
+                    worst = max(worst, float(np.abs(g[k] - rec[k]).max()))
+                assert list(g["variables"]) == out["variables"]
+            else:
+                np.savez_compressed(path, **rec)
+            print(f"{name}_ref_shim_{tag}: probs[:,1] = {out['probs'][:, 1]}, {len(out['variables'])} variables")
+    if check:
+        print(f"committed fixtures reproduce: max |diff| = {worst:.2e}")
+        assert worst < 1e-5
+
+
+if __name__ == "__main__" and "--tf-shim" in sys.argv:
+    os.makedirs(OUT, exist_ok=True)
+    tf_shim_refs(check="--check" in sys.argv)
+    sys.exit(0)
 
 if __name__ == "__main__" and "--tokenizer" not in sys.argv:
     os.makedirs(OUT, exist_ok=True)
