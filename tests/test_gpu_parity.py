@@ -100,6 +100,28 @@ def test_lxmert_against_reference_golden(tag):
     assert np.abs(xn.numpy() - g["x_norm"]).max() < (6e-3 if bool(g["trained_like"]) else 2e-3)
 
 
+@pytest.mark.parametrize("tag", ["small", "small_trained", "native"])
+@pytest.mark.parametrize("kind", ["zk", "lds"])
+def test_imagebert_against_reference_code_golden(kind, tag):
+    """CUDA zk / lds vs outputs of the reference's OWN TF-1 model code executed on the eager TensorFlow-op stand-in
+    (tests/golden/{zk,lds}_ref_shim_*.npz, tools/make_golden.py --tf-shim): native 20 x 10 shapes, 2 and 12 layers."""
+    g = np.load(os.path.join(GOLD, f"{kind}_ref_shim_{tag}.npz"))
+    cfg = ModelConfig(**ast.literal_eval(str(g["cfg"])))
+    B = int(g["batch"])
+    w = synth.make_weights(cfg, seed=int(g["seed"]), trained_like=bool(g["trained_like"]))
+    inp = synth.make_inputs(cfg, B, seed=int(g["seed"]))
+    sc = _scorer(cfg, w, B)
+    try:
+        probs, pooled = _gpu_probs(sc, inp)
+    finally:
+        sc.close()
+    err = np.abs(probs.numpy() - g["probs"]).max()
+    perr = np.abs(pooled.numpy() - g["pooled"]).max()
+    print(f"{kind} reference-code golden {tag}: max|dscore| = {err:.3e}, max|dpooled| = {perr:.3e}")
+    assert err <= (TOL_STRESS if bool(g["trained_like"]) else TOL)
+    assert perr <= (3e-2 if bool(g["trained_like"]) else 5e-3)
+
+
 @pytest.mark.parametrize("kind", [ZK, LDS, LXMERT])
 def test_full_depth_parity_and_topk_order(kind):
     """12-layer (9/5/5 for LXMERT) at the BASELINE shapes 32 x 36 x 2048: 2 queries x 12 candidates; scores within
