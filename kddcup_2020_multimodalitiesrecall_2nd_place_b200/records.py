@@ -107,8 +107,10 @@ class FeedAssembler:
     """Tokenises queries and class-label phrases (both cached: ~33 phrases, <= 1 k distinct queries per test set) and
     builds the scorer feeds of one decoded batch."""
 
-    def __init__(self, cfg: ModelConfig, tokenizer, label_map: Dict[int, str]):
-        self.cfg, self.tok = cfg, tokenizer
+    def __init__(self, cfg: ModelConfig, tokenizer, label_map: Dict[int, str], sen2forest: bool = False):
+        """sen2forest: the query rewrite of the second ImageBertB run of the ensemble (evaluate_normal_sen2fs.py:25,
+        load_data_v4.py:153-154): "sen department of" -> "forest style" before tokenisation."""
+        self.cfg, self.tok, self.sen2forest = cfg, tokenizer, sen2forest
         self._q: Dict[str, List[int]] = {}
         top = max(label_map) + 1 if label_map else 1
         self.label_table = np.zeros((top, cfg.label_len), np.int32)      # class id -> padded token ids
@@ -118,7 +120,8 @@ class FeedAssembler:
     def query_ids(self, query: str) -> List[int]:
         ids = self._q.get(query)
         if ids is None:
-            ids = self.tok.convert_tokens_to_ids(["[CLS]"] + self.tok.tokenize(query) + ["[SEP]"])
+            text = query.replace("sen department of", "forest style") if self.sen2forest else query
+            ids = self.tok.convert_tokens_to_ids(["[CLS]"] + self.tok.tokenize(text) + ["[SEP]"])
             self._q[query] = ids
         return ids
 

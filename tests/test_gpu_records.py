@@ -47,6 +47,23 @@ def test_boxes_normalize_matches_numpy_float64_division():
     assert np.array_equal(got5, want5) and np.array_equal(got4, want5[..., :4])
 
 
+def test_zk_feeds_match_the_reference_loader_golden(tmp_path):
+    """The zk feeds of FeedAssembler.assemble — GPU box normalisation + area included — against what the reference's
+    own read_line / seq_padding_2 produce for the same TSV lines (tests/golden/records_kat.npz): bit-exact."""
+    g = np.load(os.path.join(GOLD, "records_kat.npz"))
+    lines = [str(x).encode("utf-8") for x in g["lines"]]
+    out = records.decode_lines(lines, max_boxes=10, pin=False)
+    (tmp_path / "labels.txt").write_text("\n".join(str(x) for x in g["label_lines"]) + "\n", encoding="utf-8")
+    tok = tokenizer.FullTokenizer(vocab={str(t): i for i, t in enumerate(g["vocab"])})
+    cfg = ModelConfig(ZK, n_layers=1, lq=20, nbox=10, vocab=len(g["vocab"]))
+    feeds = records.FeedAssembler(cfg, tok, records.load_label_map(str(tmp_path / "labels.txt"))).assemble(out)
+    assert np.array_equal(feeds["boxes"].cpu().numpy(), g["boxes5_padded"])
+    for i in range(len(lines)):
+        ids = g[f"s2f0_{i}_query_ids"].tolist()
+        assert feeds["len_query"][i].item() == min(len(ids), 20)
+        assert feeds["num_boxes"][i].item() == min(int(g[f"s2f0_{i}_scalars"][3]), 10)
+
+
 @pytest.mark.parametrize("kind", [ZK, LXMERT])
 def test_tsv_to_scores_against_oracle(kind):
     from kddcup_2020_multimodalitiesrecall_2nd_place_b200.scorer import MatchScorer

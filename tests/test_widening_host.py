@@ -91,6 +91,40 @@ def test_decode_matches_reference_read_line_bit_exact(threads):
         assert np.array_equal(out["class_labels"][i, :k].numpy(), labels[:k]) and not out["class_labels"][i, k:].any()
 
 
+def test_decode_and_feed_assembly_match_the_reference_loader_golden(tmp_path):
+    """tests/golden/records_kat.npz = outputs of the reference's OWN read_line / seq_padding / seq_padding_2 and label
+    cleaning loop (code/imagebert_zk/load_data_v4.py, extracted by name by tools/make_golden.py --records, run with the
+    reference's own tokenizer) on 8 synthetic TSV lines, one of them over the 10-box budget; both values of the
+    sen2forest flag.  The C++ decoder, the tokenizer, the label-phrase table and the feed assembly against it."""
+    g = np.load(os.path.join(GOLD, "records_kat.npz"))
+    lines = [str(x).encode("utf-8") for x in g["lines"]]
+    out = records.decode_lines(lines, max_boxes=10, n_threads=2, pin=False)
+    (tmp_path / "multimodal_labels.txt").write_text("\n".join(str(x) for x in g["label_lines"]) + "\n", encoding="utf-8")
+    label_map = records.load_label_map(str(tmp_path / "multimodal_labels.txt"))
+    tok = tokenizer.FullTokenizer(vocab={str(t): i for i, t in enumerate(g["vocab"])})
+    cfg = ModelConfig("imagebert_lds", n_layers=1, lq=20, nbox=10, vocab=len(g["vocab"]))   # (zk adds boxes: GPU test)
+    feeds = {f: records.FeedAssembler(cfg, tok, label_map, sen2forest=bool(f)).assemble(out) for f in (0, 1)}
+    for i in range(len(lines)):
+        pid, h, w, nb, qid = g[f"s2f0_{i}_scalars"].tolist()
+        k = min(nb, 10)
+        assert (out["product_id"][i], out["image_h"][i], out["image_w"][i], out["num_boxes"][i], out["query_id"][i]) \
+            == (pid, h, w, nb, qid)
+        assert np.array_equal(out["feats"][i, :k].numpy().view(np.uint32), g[f"s2f0_{i}_feats_u32"][:k])
+        # raw boxes: the reference only keeps the normalised ones (float32 boxes / python ints = a float64 division)
+        b4 = out["boxes4"][i, :k].numpy().astype(np.float64)
+        want5 = g[f"s2f0_{i}_boxes5"][:k]
+        assert np.array_equal((b4 / [h, w, h, w]).astype(np.float32), want5[:, :4])
+        for f in (0, 1):
+            ids = g[f"s2f{f}_{i}_query_ids"].tolist()
+            assert feeds[f]["query_ids"][i].tolist() == (ids + [0] * 20)[:20]
+            assert feeds[f]["label_ids"][i, :k].tolist() == g[f"s2f{f}_{i}_label_ids"][:k].tolist()
+            assert not feeds[f]["label_ids"][i, k:].any()
+    assert str(g["s2f1_1_query"]) == "forest style dress" and str(g["s2f0_1_query"]) == "sen department of dress"
+    assert feeds[1]["query_ids"][1].tolist() != feeds[0]["query_ids"][1].tolist()
+    # the zero-padded feature block of the feeds (seq_padding_2 to the box budget, load_data_v4.py:380-383)
+    assert np.array_equal(out["feats"].numpy().view(np.uint32), g["feats_padded_u32"])
+
+
 def test_decode_edge_cases_and_errors():
     from kddcup_2020_multimodalitiesrecall_2nd_place_b200._lib import MmrError
     assert records.decode_lines([], pin=False)["queries"] == []

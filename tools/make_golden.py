@@ -221,6 +221,88 @@ def tf_shim_refs(check=False):
         assert worst < 1e-5
 
 
+# ---------------------------------------------------------------------------------------------- record decode KAT
+def records_kat():
+    """The reference's OWN per-line loader — read_line, seq_padding, and the label-phrase cleaning loop of
+    code/imagebert_zk/load_data_v4.py (133-163, 74-85, 34-38), extracted by name (importing the module would read the
+    competition data at import time) and run with the reference's own tokenizer class — on synthetic TSV lines."""
+    import ast
+    import base64
+    import importlib.util
+    import tempfile
+    import types
+    rng = np.random.default_rng(11)
+    vocab = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"] + list("abcdefghijklmnopqrstuvwxyz0123456789'-") + \
+            ["women", "men", "leather", "shoes", "dress", "kids", "wash", "basin", "forest", "style", "sen", "department",
+             "of", "bag", "hand", "##s", "##ing", "top", "t", "shirt", "others", "red", "black", "连", "衣", "裙"]
+    label_lines = ["0\ttop, t-shirt (women)", "1\tleather shoes.", "2\tkids", "3\thand bag, bag", "4\tothers",
+                   "5\twash basin", "6\tred black dress for women and men and kids and others"]
+    queries = ["women's leather shoes", "sen department of dress", "kids wash basin red", "连衣裙 black", "bag",
+               "men t-shirt top forest style others", "red dress", "hand bag for women and men and kids and others red"]
+    lines = []
+    for i, q in enumerate(queries):
+        nb = [1, 2, 3, 12, 2, 1, 3, 2][i]           # 12 > the 10-box budget of the feeds
+        h, w = int(rng.integers(200, 900)), int(rng.integers(200, 900))
+        boxes = np.round(rng.random((nb, 4)) * 500).astype(np.float32)
+        feats = (np.arange(nb * 2048, dtype=np.float32).reshape(nb, 2048) % 17) * 0.125 * (i + 1)   # compressible
+        labels = rng.integers(0, 7, nb).astype(np.int64)
+        fields = [str(1000 + i), str(h), str(w), str(nb), base64.b64encode(boxes.tobytes()).decode(),
+                  base64.b64encode(feats.tobytes()).decode(), base64.b64encode(labels.tobytes()).decode(), q, str(7 * i)]
+        lines.append("\t".join(fields) + "\n")
+    tf = types.ModuleType("tensorflow")
+    tf.gfile = types.SimpleNamespace(GFile=lambda p, m="r": open(p, m, encoding="utf-8"))
+    sys.modules["tensorflow"] = tf
+    spec = importlib.util.spec_from_file_location("ref_tok_zk2", os.path.join(REF, "code/imagebert_zk/tokenization.py"))
+    tokmod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tokmod)
+    src = open(os.path.join(REF, "code/imagebert_zk/load_data_v4.py")).read()
+    tree = ast.parse(src)
+    fns = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("read_line", "seq_padding", "seq_padding_2")]
+    label_loop = [n for n in tree.body if isinstance(n, ast.For) and "multimodal_labels" in ast.get_source_segment(src, n)]
+    assert len(fns) == 3 and len(label_loop) == 1
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, "data"))
+        os.makedirs(os.path.join(d, "work"))
+        with open(os.path.join(d, "data", "multimodal_labels.txt"), "w", encoding="utf-8") as f:
+            f.write("\n".join(label_lines) + "\n")
+        vf = os.path.join(d, "vocab.txt")
+        with open(vf, "w", encoding="utf-8") as f:
+            f.write("\n".join(vocab) + "\n")
+        ns = {"np": np, "base64": base64, "dict_multimodal_labels": {}, "FLAGS": types.SimpleNamespace(sen2forest=0),
+              "tokenizer": tokmod.FullTokenizer(vocab_file=vf, do_lower_case=True)}
+        os.chdir(os.path.join(d, "work"))
+        try:
+            exec(compile(ast.Module(body=label_loop + fns, type_ignores=[]), "load_data_v4.py", "exec"), ns)
+        finally:
+            os.chdir(cwd)
+    out = {"lines": np.array(lines), "vocab": np.array(vocab), "label_lines": np.array(label_lines)}
+    for flag in (0, 1):                             # evaluate_normal.py / evaluate_normal_sen2fs.py
+        ns["FLAGS"].sen2forest = flag
+        rec = [ns["read_line"](ln) for ln in lines]
+        for i, r in enumerate(rec):
+            pid, h, w, nb, boxes5, feats, idx_labels, len_labels, idx_query, qid, query, str_labels = r
+            pre = f"s2f{flag}_{i}_"
+            out[pre + "scalars"] = np.array([pid, h, w, nb, qid], np.int64)
+            out[pre + "boxes5"] = boxes5
+            out[pre + "feats_u32"] = np.ascontiguousarray(feats).view(np.uint32)
+            out[pre + "label_ids"] = np.asarray(idx_labels, np.int64)
+            out[pre + "label_lens"] = np.asarray(len_labels, np.int64)
+            out[pre + "query_ids"] = np.asarray(idx_query, np.int64)
+            out[pre + "query"] = np.array(query)
+    # the batch padding of the feeds (load_data_v4.py:380-389): seq_padding_2 to 10 boxes, zero padding
+    rec = [ns["read_line"](ln) for ln in lines]
+    out["feats_padded_u32"] = np.ascontiguousarray(ns["seq_padding_2"]([r[5] for r in rec], 10, 0).astype(np.float32)).view(np.uint32)
+    out["boxes5_padded"] = ns["seq_padding_2"]([r[4] for r in rec], 10, 0).astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "records_kat.npz"), **out)
+    print("records_kat:", len(lines), "lines,", os.path.getsize(os.path.join(OUT, "records_kat.npz")), "bytes")
+
+
+if __name__ == "__main__" and "--records" in sys.argv:
+    os.makedirs(OUT, exist_ok=True)
+    records_kat()
+    sys.exit(0)
+
 if __name__ == "__main__" and "--tf-shim" in sys.argv:
     os.makedirs(OUT, exist_ok=True)
     tf_shim_refs(check="--check" in sys.argv)
