@@ -7,7 +7,8 @@ The product (kddcup_2020_multimodalitiesrecall_2nd_place_b200) never imports it 
 
 Pinning status
   * ensemble (code/main.py) and nDCG@5: pinned by the reference's shipped files — tests/golden/ensemble_kat and
-    the nDCG known answer 0.7098 (kdd-report-final.pdf table 5) reproduced from shipped score files.
+    the nDCG known answer 0.7098 (kdd-report-final.pdf table 5) reproduced from shipped score files — and nDCG@k
+    also by the reference's own evaluation.py run on seeded synthetic rankings (tests/golden/ndcg_ref_cases.json).
   * LXMERT: pinned against the reference's OWN PyTorch code, imported from /root/reference in the dev container
     (oracle/lxmert_ref.py); golden vectors generated from it are committed under tests/golden/ with the script.
   * ImageBert zk / lds: TF-1.12 + Python 2 are not installable, and the reference ships no activations or weights.

@@ -45,6 +45,17 @@ def test_ndcg_known_answer():
     assert abs(val - 0.7098) < 5e-5, val
 
 
+def test_ndcg_matches_the_reference_evaluation_code():
+    """oracle nDCG@k vs the reference's own evaluation.py (tests/golden/ndcg_ref_cases.json, tools/make_golden.py --ndcg):
+    ties, fewer candidates than k, ground truth absent from the candidates."""
+    import json
+    g = json.load(open(os.path.join(GOLD, "ndcg_ref_cases.json")))
+    for c in g["cases"]:
+        pred = {q: [p for p, _ in sorted(v, key=lambda t: t[1], reverse=True)] for q, v in c["pred"].items()}
+        ans = {q: {str(x) for x in v} for q, v in c["answers"].items()}
+        assert abs(ensemble.ndcg_at_k(pred, ans, c["k"]) - c["ndcg"]) < 1e-12
+
+
 def _digest(w):
     h = hashlib.sha256()
     for k in sorted(w):

@@ -298,6 +298,44 @@ def records_kat():
     print("records_kat:", len(lines), "lines,", os.path.getsize(os.path.join(OUT, "records_kat.npz")), "bytes")
 
 
+# ---------------------------------------------------------------------------------------------- nDCG@k by the reference's evaluation.py
+def ndcg_ref_cases():
+    """The reference's OWN evaluate(..., 'ndcg', valid_answer, k) (code/imagebert_lds/src/evaluation.py:4-38, imported as
+    is; numpy >= 2 dropped np.asfarray, which is given back as np.asarray(float)) on seeded synthetic rankings."""
+    import importlib.util
+    import json
+    import tempfile
+    if not hasattr(np, "asfarray"):
+        np.asfarray = lambda a, dtype=float: np.asarray(a, dtype=dtype)
+    spec = importlib.util.spec_from_file_location("ref_evaluation", os.path.join(REF, "code/imagebert_lds/src/evaluation.py"))
+    ev = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ev)
+    rng = np.random.default_rng(21)
+    cases = []
+    for ci, (nq, ncand, k) in enumerate([(7, 30, 5), (5, 3, 5), (9, 12, 3), (4, 40, 10)]):
+        pred, ans = {}, {}
+        for q in range(nq):
+            pids = rng.permutation(1000)[:ncand]
+            scores = np.round(rng.random(ncand), 3)            # ties on purpose: list.sort is stable
+            pred[str(q)] = [[str(int(p)), float(s)] for p, s in zip(pids, scores)]
+            n_gt = int(rng.integers(1, 8))
+            gt = list(rng.choice(pids, size=min(n_gt, ncand), replace=False)) + ([1234567] if q % 3 == 0 else [])
+            ans[str(q)] = [int(x) for x in gt]
+        with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as f:
+            json.dump(ans, f)
+        val = ev.evaluate(None, None, {q: [list(x) for x in v] for q, v in pred.items()}, "ndcg", f.name, k)
+        os.unlink(f.name)
+        cases.append({"k": k, "pred": pred, "answers": ans, "ndcg": float(val)})
+        print(f"ndcg_ref case {ci}: k={k} ndcg={val:.6f}")
+    json.dump({"source": "code/imagebert_lds/src/evaluation.py evaluate(..., 'ndcg', ...)", "cases": cases},
+              open(os.path.join(OUT, "ndcg_ref_cases.json"), "w"))
+
+
+if __name__ == "__main__" and "--ndcg" in sys.argv:
+    os.makedirs(OUT, exist_ok=True)
+    ndcg_ref_cases()
+    sys.exit(0)
+
 if __name__ == "__main__" and "--records" in sys.argv:
     os.makedirs(OUT, exist_ok=True)
     records_kat()
