@@ -144,14 +144,16 @@ zk_region_sum_kernel(const float* __restrict__ feat32, const float* __restrict__
 //           are summed in position order — the same order, hence the same bits, as zk_region_sum_kernel
 //   sum     zk_region_sum_rep_kernel: feat + term[rep] / 8 + box FC, per box
 // Which box wins a slot is a race; the value it computes is not.  The table is never cleared: entries carry the
-// forward's epoch and older ones count as empty.
+// forward's epoch and older ones count as empty.  The epoch lives in DEVICE memory (read by the claim kernel, moved
+// on by the sum kernel, the last of the three): a forward replayed from a CUDA graph sees a fresh epoch too.
 __global__ void __launch_bounds__(256)
 zk_label_claim_kernel(const int32_t* __restrict__ label_ids, int rows, unsigned long long* __restrict__ tab,
-                      uint32_t tab_mask, uint32_t epoch, int32_t* __restrict__ rep) {
+                      uint32_t tab_mask, const uint32_t* __restrict__ epoch_ptr, int32_t* __restrict__ rep) {
   pdl_wait();
   pdl_launch_dependents();
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= rows) return;
+  const uint32_t epoch = *reinterpret_cast<const volatile uint32_t*>(epoch_ptr);
   const int4* ids4 = reinterpret_cast<const int4*>(label_ids);
   const int4 a = __ldg(ids4 + 2 * int64_t(row)), b = __ldg(ids4 + 2 * int64_t(row) + 1);
   uint32_t hsh = 2166136261u;
@@ -220,9 +222,13 @@ __global__ void __launch_bounds__(256)
 zk_region_sum_rep_kernel(const float* __restrict__ feat32, const float* __restrict__ boxes5,
                          const int32_t* __restrict__ rep, const float* __restrict__ term32,
                          const float* __restrict__ Wb, const float* __restrict__ bb,
-                         typename E16::T* __restrict__ out16, int rows) {
+                         typename E16::T* __restrict__ out16, int rows, uint32_t* __restrict__ epoch_ptr) {
   pdl_wait();
   pdl_launch_dependents();
+  if (blockIdx.x == 0 && threadIdx.x == 0) {   // claim and term kernels of this forward are complete (stream order)
+    const uint32_t next = *epoch_ptr + 1u;
+    *epoch_ptr = next == 0u ? 1u : next;       // 0 = "never written"
+  }
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -527,10 +533,10 @@ mmr_status zk_region_sum(const float* feat32, const float* boxes5, const int32_t
 }
 
 mmr_status zk_label_terms(const int32_t* label_ids, const float* tables, int vocab, const float* bc1,
-                          unsigned long long* tab, uint32_t tab_mask, uint32_t epoch, int32_t* rep, float* term32,
-                          int rows, cudaStream_t st) {
+                          unsigned long long* tab, uint32_t tab_mask, const uint32_t* epoch_dev, int32_t* rep,
+                          float* term32, int rows, cudaStream_t st) {
   (void)launch_pdl(zk_label_claim_kernel, dim3((rows + 255) / 256), dim3(256), 0, st, label_ids, rows, tab, tab_mask,
-                   epoch, rep);
+                   epoch_dev, rep);
   MMR_CUDA_OK(cudaGetLastError());
   (void)launch_pdl(zk_label_term_kernel, dim3(rows), dim3(256), 0, st, label_ids, tables, vocab, bc1,
                    static_cast<const int32_t*>(rep), term32);
@@ -538,9 +544,10 @@ mmr_status zk_label_terms(const int32_t* label_ids, const float* tables, int voc
   return MMR_OK;
 }
 mmr_status zk_region_sum_rep(const float* feat32, const float* boxes5, const int32_t* rep, const float* term32,
-                             const float* Wb, const float* bb, void* out16, int rows, int dtype, cudaStream_t st) {
+                             const float* Wb, const float* bb, void* out16, int rows, uint32_t* epoch_dev, int dtype,
+                             cudaStream_t st) {
   MMR_DISPATCH16(dtype, ((void)launch_pdl(zk_region_sum_rep_kernel<E16>, dim3(blocks_for(rows)), dim3(256), 0, st,
-                            feat32, boxes5, rep, term32, Wb, bb, static_cast<typename E16::T*>(out16), rows)));
+                            feat32, boxes5, rep, term32, Wb, bb, static_cast<typename E16::T*>(out16), rows, epoch_dev)));
   MMR_CUDA_OK(cudaGetLastError());
   return MMR_OK;
 }

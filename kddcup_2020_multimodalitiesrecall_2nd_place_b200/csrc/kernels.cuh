@@ -46,10 +46,11 @@ mmr_status zk_region_sum(const float* feat32, const float* boxes5, const int32_t
                          int dtype, cudaStream_t st);
 // label term once per distinct label phrase of the batch (claim + term kernels), then the per-box sum
 mmr_status zk_label_terms(const int32_t* label_ids, const float* tables, int vocab, const float* bc1,
-                          unsigned long long* tab, uint32_t tab_mask, uint32_t epoch, int32_t* rep, float* term32,
-                          int rows, cudaStream_t st);
+                          unsigned long long* tab, uint32_t tab_mask, const uint32_t* epoch_dev, int32_t* rep,
+                          float* term32, int rows, cudaStream_t st);
 mmr_status zk_region_sum_rep(const float* feat32, const float* boxes5, const int32_t* rep, const float* term32,
-                             const float* Wb, const float* bb, void* out16, int rows, int dtype, cudaStream_t st);
+                             const float* Wb, const float* bb, void* out16, int rows, uint32_t* epoch_dev, int dtype,
+                             cudaStream_t st);
 mmr_status zk_embed(const int32_t* query_ids, const int32_t* segment_ids, const float* region32,
                     const int32_t* len_query, const int32_t* num_boxes, const float* E, const float* T,
                     const float* P, const float* gamma, const float* beta, int Lq, int R, int B, void* x16,

@@ -162,7 +162,8 @@ struct mmr_handle {
   float *tmp32 = nullptr, *x32 = nullptr, *pooled32 = nullptr, *head32 = nullptr, *emb_tap = nullptr;
   // zk: label term once per distinct phrase (embed.cu): phrase table {epoch, row}, representative of every box, terms
   unsigned long long* lab_tab = nullptr;
-  uint32_t lab_tab_mask = 0, lab_epoch = 0;
+  uint32_t lab_tab_mask = 0;
+  uint32_t* lab_epoch_dev = nullptr;   // device-resident: moved on by the forward itself (CUDA-graph replay safe)
   int32_t* lab_rep = nullptr;
   float* lab_term32 = nullptr;
   float* layer_tap = nullptr;   // [n_layers, rows_max, hidden], allocated by mmr_set_debug_taps(h, 2)
@@ -500,6 +501,7 @@ static mmr_status alloc_workspace(mmr_handle* h) {
     add(size_t(lab_slots) * 8);   // lab_tab
     add(B * R * 4);               // lab_rep
     add(B * R * H * 4);           // lab_term32
+    add(256);                     // lab_epoch_dev
   }
   bytes += 4096;
   MMR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->work.base), bytes));
@@ -522,9 +524,12 @@ static mmr_status alloc_workspace(mmr_handle* h) {
     h->lab_tab = static_cast<unsigned long long*>(h->work.take(size_t(lab_slots) * 8));
     h->lab_rep = static_cast<int32_t*>(h->work.take(B * R * 4));
     h->lab_term32 = static_cast<float*>(h->work.take(B * R * H * 4));
-    if (!h->lab_term32) return fail(MMR_ERR_NOMEM, "workspace arena mis-sized (label terms)");
+    h->lab_epoch_dev = static_cast<uint32_t*>(h->work.take(256));
+    if (!h->lab_term32 || !h->lab_epoch_dev) return fail(MMR_ERR_NOMEM, "workspace arena mis-sized (label terms)");
     h->lab_tab_mask = lab_slots - 1;
     MMR_CUDA_OK(cudaMemset(h->lab_tab, 0, size_t(lab_slots) * 8));   // epoch 0 = never written
+    const uint32_t first_epoch = 1;
+    MMR_CUDA_OK(cudaMemcpy(h->lab_epoch_dev, &first_epoch, sizeof(first_epoch), cudaMemcpyHostToDevice));
   }
   return MMR_OK;
 }
@@ -683,13 +688,12 @@ static mmr_status forward_single_stream(Ctx& c, const mmr_inputs* in, int B, flo
       MMR_TRY(c.G(h->f16, cfg.feat_dim, h->conv2, B * R, nullptr, nullptr, 0, h->tmp32, MMR_ACT_RELU));
       // (the claim kernel reads the 8 ids of a box as two 16-byte words)
       if (tuning(MMR_TUNE_LABEL_DEDUP) != 0 && (reinterpret_cast<uintptr_t>(in->label_ids) & 15) == 0) {
-        if (++h->lab_epoch == 0) h->lab_epoch = 1;
-        MMR_TRY(zk_label_terms(in->label_ids, h->tables, cfg.vocab, h->bc1, h->lab_tab, h->lab_tab_mask, h->lab_epoch,
+        MMR_TRY(zk_label_terms(in->label_ids, h->tables, cfg.vocab, h->bc1, h->lab_tab, h->lab_tab_mask, h->lab_epoch_dev,
                                h->lab_rep, h->lab_term32, B * R, c.st));
         MMR_TRY(c.mark(K_ROW, 0));
         MMR_TRY(c.mark(K_ROW, 0));
-        MMR_TRY(zk_region_sum_rep(h->tmp32, in->boxes, h->lab_rep, h->lab_term32, h->Wb, h->bb, h->t16, B * R, c.dt,
-                                  c.st));
+        MMR_TRY(zk_region_sum_rep(h->tmp32, in->boxes, h->lab_rep, h->lab_term32, h->Wb, h->bb, h->t16, B * R,
+                                  h->lab_epoch_dev, c.dt, c.st));
       } else {
         MMR_TRY(zk_region_sum(h->tmp32, in->boxes, in->label_ids, h->tables, cfg.vocab, h->bc1, h->Wb, h->bb, h->t16,
                               B * R, c.dt, c.st));

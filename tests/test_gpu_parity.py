@@ -343,3 +343,43 @@ def test_lxmert_two_stream_merged_launches(B, lq):
     finally:
         _lib.check(lib.mmr_set_tuning(_lib.TUNE_LX_MERGE, 1))
         sc.close()
+
+
+@pytest.mark.parametrize("kind", [ZK, LXMERT])
+def test_forward_replays_from_a_cuda_graph(kind):
+    """mmr_forward neither allocates nor synchronises, and the state it keeps between forwards (the LayerNorm exchange
+    epoch, the label-phrase table epoch) lives on the device: a forward captured into a CUDA graph replays on new
+    inputs (different label phrases included) with the bits of an eager forward."""
+    cfg = _small_cfg(kind)
+    w = synth.make_weights(cfg, seed=synth.SEED0 + 13)
+    B = 16
+    sc = _scorer(cfg, w, B)
+    try:
+        sets = []
+        for i in range(3):
+            inp = synth.make_inputs(cfg, B, seed=synth.SEED0 + 100 + i, n_queries=2)
+            if i == 2:
+                ids = np.array(inp["label_ids"], copy=True)
+                ids[...] = np.random.default_rng(i).integers(1, cfg.vocab, size=ids.shape)
+                inp = dict(inp, label_ids=ids.astype(np.int32))
+            sets.append({k: v.cuda() for k, v in sc.to_feeds(inp).items()})
+        eager = [sc.forward_device(f).clone() for f in sets]
+        torch.cuda.synchronize()
+        static = {k: v.clone() for k, v in sets[0].items()}
+        out = torch.empty((B, 2), dtype=torch.float32, device="cuda")
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            sc.forward_device(static, probs_out=out)          # warm-up on the capture stream
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                sc.forward_device(static, probs_out=out)
+        for rounds in range(2):
+            for f, want in zip(sets, eager):
+                for k in static:
+                    static[k].copy_(f[k])
+                g.replay()
+                torch.cuda.synchronize()
+                assert torch.equal(out, want)
+    finally:
+        sc.close()
