@@ -88,6 +88,8 @@ enum { MMR_TUNE_GEMM_PAIR = 0, MMR_TUNE_GEMM_P16 = 1, MMR_TUNE_GEMM_TAIL = 2, MM
 mmr_status mmr_set_tuning(int knob, int value);
 /* Current value of a knob (-1 for an unknown one). */
 int mmr_get_tuning(int knob);
+/* Counts mmr_set_tuning calls: a caller that replays captured CUDA graphs of mmr_forward re-captures when it moves. */
+unsigned mmr_tuning_generation(void);
 /* MMR_OK iff `device` is an sm_100 part. */
 mmr_status mmr_device_check(int device);
 

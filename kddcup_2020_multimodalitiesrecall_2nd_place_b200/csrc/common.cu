@@ -21,6 +21,7 @@ mmr_status fail(mmr_status code, const char* fmt, ...) {
 // knob -> {environment variable, default}
 static int g_tuning[MMR_TUNE_COUNT];
 static bool g_tuning_init = false;
+static unsigned g_tuning_generation = 0;   // bumped by mmr_set_tuning: captured CUDA graphs of a forward are keyed on it
 static void tuning_init() {
   static const struct { const char* env; int def; } spec[MMR_TUNE_COUNT] = {
       {"MMR_GEMM_PAIR", 1}, {"MMR_GEMM_P16", 1}, {"MMR_GEMM_TAIL", 1}, {"MMR_GEMM_CLUSTER", 1}, {"MMR_GEMM_LN", 1}, {"MMR_PDL", 1}, {"MMR_ATTN_TMA", 0}, {"MMR_ATTN_TC", 2}, {"MMR_LN_ROW_CFG", 0}, {"MMR_LABEL_DEDUP", 1}, {"MMR_LX_MERGE", 1}};
@@ -68,8 +69,10 @@ extern "C" mmr_status mmr_set_tuning(int knob, int value) {
   if (knob < 0 || knob >= MMR_TUNE_COUNT) return mmr::fail(MMR_ERR_INVALID, "mmr_set_tuning: unknown knob %d", knob);
   if (!mmr::g_tuning_init) mmr::tuning_init();
   mmr::g_tuning[knob] = value;
+  ++mmr::g_tuning_generation;
   return MMR_OK;
 }
+extern "C" unsigned mmr_tuning_generation(void) { return mmr::g_tuning_generation; }
 extern "C" int mmr_get_tuning(int knob) { return (knob >= 0 && knob < MMR_TUNE_COUNT) ? mmr::tuning(knob) : -1; }
 extern "C" mmr_status mmr_device_check(int device) {
   int n = 0;

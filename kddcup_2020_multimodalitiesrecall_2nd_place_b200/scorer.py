@@ -12,6 +12,7 @@ Reference call sites replaced (the per-batch body of the three scoring drivers):
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -82,6 +83,14 @@ class MatchScorer:
         self._h = h
         self.spec = feed_spec(cfg)
         self._slots = None
+        # CUDA graphs of the forward, keyed on (batch, every pointer, tuning generation): the second forward on the
+        # same buffers is captured, later ones are replayed (the 69 launches of a forward then cost one graph launch;
+        # +2 % on the 12-layer forward).  mmr_forward neither allocates nor synchronises and keeps its state on the
+        # device, which is what makes the replay exact (tests/test_gpu_parity.py).  MMR_CUDA_GRAPHS=0 turns it off.
+        self.use_graphs = os.environ.get("MMR_CUDA_GRAPHS", "1") != "0"
+        self._graphs, self._seen = {}, set()
+        self._capture_stream = None
+        self._taps_on = self._profiling_on = False
 
     # ------------------------------------------------------------------ lifetime
     def close(self):
@@ -120,12 +129,40 @@ class MatchScorer:
                     or not fused.is_contiguous():
                 raise ValueError("feed 'region_sum': need contiguous float32 [B, nbox, hidden]")
             inp.region_sum = fused.data_ptr()
+        caller_owns_output = probs_out is not None
         if probs_out is None:
             probs_out = torch.empty((B, 2), dtype=torch.float32, device=self.device)
-        _lib.check(self.lib.mmr_forward(self._h, C.byref(inp), B, probs_out.data_ptr(),
-                                        0 if logits_out is None else logits_out.data_ptr(),
-                                        0 if pooled_out is None else pooled_out.data_ptr(),
-                                        torch.cuda.current_stream(self.device).cuda_stream))
+
+        def launch():
+            _lib.check(self.lib.mmr_forward(self._h, C.byref(inp), B, probs_out.data_ptr(),
+                                            0 if logits_out is None else logits_out.data_ptr(),
+                                            0 if pooled_out is None else pooled_out.data_ptr(),
+                                            torch.cuda.current_stream(self.device).cuda_stream))
+
+        if not (self.use_graphs and caller_owns_output and not self._taps_on and not self._profiling_on) \
+                or torch.cuda.is_current_stream_capturing():
+            launch()
+            return probs_out
+        key = (B, int(self.lib.mmr_tuning_generation()), probs_out.data_ptr(),
+               0 if logits_out is None else logits_out.data_ptr(), 0 if pooled_out is None else pooled_out.data_ptr(),
+               tuple(int(getattr(inp, f[0]) or 0) for f in inp._fields_))
+        g = self._graphs.get(key)
+        if g is None:
+            if key not in self._seen or len(self._graphs) >= 64:
+                self._seen.add(key)            # first forward on these buffers: eager (also warms every lazy init)
+                launch()
+                return probs_out
+            if self._capture_stream is None:
+                self._capture_stream = torch.cuda.Stream(self.device)
+            cur = torch.cuda.current_stream(self.device)
+            self._capture_stream.wait_stream(cur)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(self._capture_stream):
+                with torch.cuda.graph(g, stream=self._capture_stream):
+                    launch()
+            cur.wait_stream(self._capture_stream)
+            self._graphs[key] = g
+        g.replay()
         return probs_out
 
     def launches_per_forward(self) -> int:
@@ -133,6 +170,7 @@ class MatchScorer:
 
     def set_profiling(self, on: bool):
         """Per-launch CUDA-event timing inside forward_device (bench.py's roofline line)."""
+        self._profiling_on = bool(on)
         _lib.check(self.lib.mmr_set_profiling(self._h, int(on)))
 
     def profile(self):
@@ -146,6 +184,7 @@ class MatchScorer:
 
     def set_debug_taps(self, level):
         """0 off, 1 keep the embedding output, 2 also keep every encoder layer's output (single-stream models)."""
+        self._taps_on = int(level) != 0
         _lib.check(self.lib.mmr_set_debug_taps(self._h, int(level)))
 
     def activation(self, which: int, batch: int) -> torch.Tensor:
@@ -175,7 +214,8 @@ class MatchScorer:
             self._slots = []
             for _ in range(2):
                 dev = {n: torch.empty((Bm, *shape), dtype=dt, device=self.device) for n, (dt, shape) in self.spec.items()}
-                self._slots.append({"dev": dev, "free": torch.cuda.Event(), "ready": torch.cuda.Event()})
+                self._slots.append({"dev": dev, "free": torch.cuda.Event(), "ready": torch.cuda.Event(),
+                                    "probs": torch.empty((Bm, 2), dtype=torch.float32, device=self.device)})
             self._copy_stream = torch.cuda.Stream(self.device)
         return self._slots
 
@@ -204,7 +244,9 @@ class MatchScorer:
                     s["dev"][name][: hi - lo].copy_(feeds_host[name][lo:hi], non_blocking=True)
                 s["ready"].record(copy)
             compute.wait_event(s["ready"])
-            self.forward_device({n: s["dev"][n][: hi - lo] for n in self.spec}, probs_out=dev_probs[lo:hi])
+            # into the slot's own probs buffer: the forward then sees the same pointers every other chunk (graph replay)
+            self.forward_device({n: s["dev"][n][: hi - lo] for n in self.spec}, probs_out=s["probs"][: hi - lo])
+            dev_probs[lo:hi].copy_(s["probs"][: hi - lo], non_blocking=True)
             s["free"].record(compute)
         out.copy_(dev_probs, non_blocking=True)
         compute.synchronize()
