@@ -97,7 +97,7 @@ class NvmlThreadSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.02)
 
     def start(self):
         if self.nv is not None:
@@ -115,11 +115,11 @@ class NvmlThreadSampler:
 
 
 class ClockSampler:
-    """SM clock and throttle reasons DURING the timed region, sampled by a separate `nvidia-smi -lms` process (the
-    profiling recipe's clocks line): it keeps NVML calls out of the process that launches the kernels.  (An A/B at
-    N = 1 measured no difference between this and an in-process NVML thread: 69.2 vs 69.1 k pairs/s.)  The
-    subprocess is started before the barrier and only its samples stamped inside [start(), stop()] are used.  Falls
-    back to the in-process NVML thread when nvidia-smi is not usable."""
+    """SM clock and throttle reasons DURING the timed region.  Primary source: an NVML poll (every 20 ms) from a thread
+    of this process — an A/B at N = 1 measured no cost (69.1 vs 69.2 k pairs/s against an out-of-process sampler).
+    Fall-back when pynvml is not usable: a separate `nvidia-smi -lms 50` process (the profiling recipe's clocks line),
+    started before the barrier, of which only the samples stamped inside [start(), stop()] are used (it delivered a
+    single sample inside a 360 ms region at N = 2, which is why it is not the primary)."""
 
     FIELDS = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -133,7 +133,13 @@ class ClockSampler:
         self.proc, self.fallback = None, None
         self.t0 = self.t1 = None
         exe = shutil.which("nvidia-smi")
-        if exe is not None and os.environ.get("MMR_BENCH_SAMPLER", "smi") == "smi":
+        mode = os.environ.get("MMR_BENCH_SAMPLER", "nvml")
+        if mode == "nvml":
+            nv = NvmlThreadSampler(index)
+            if nv.nv is not None or exe is None:
+                self.fallback = nv
+                return
+        if exe is not None:
             self.log = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             try:
                 self.proc = subprocess.Popen([exe, "-i", str(index), f"--query-gpu={self.FIELDS}",
