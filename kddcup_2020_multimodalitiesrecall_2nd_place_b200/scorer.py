@@ -94,6 +94,9 @@ class MatchScorer:
 
     # ------------------------------------------------------------------ lifetime
     def close(self):
+        if getattr(self, "_graphs", None):
+            self._graphs.clear()               # captured forwards point into the workspace that goes away below
+            self._seen.clear()
         if getattr(self, "_h", None):
             self.lib.mmr_destroy(self._h)
             self._h = None
