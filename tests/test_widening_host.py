@@ -125,6 +125,36 @@ def test_decode_and_feed_assembly_match_the_reference_loader_golden(tmp_path):
     assert np.array_equal(out["feats"].numpy().view(np.uint32), g["feats_padded_u32"])
 
 
+def test_lxmert_feeds_match_the_reference_loader_golden(tmp_path):
+    """tests/golden/records_kat_lxmert.npz = the same TSV lines through the LXMERT tree's OWN read_line / seq_padding /
+    seq_padding_2 (code/lxmert/src/utils.py, extracted by name) with its own BertTokenizer: query ids and mask at 23
+    tokens, label-phrase ids, visual mask, and the 4-d boxes as float32(float64 division)."""
+    g0 = np.load(os.path.join(GOLD, "records_kat.npz"))
+    g = np.load(os.path.join(GOLD, "records_kat_lxmert.npz"))
+    lines = [str(x).encode("utf-8") for x in g0["lines"]]
+    out = records.decode_lines(lines, max_boxes=10, n_threads=1, pin=False)
+    (tmp_path / "labels.txt").write_text("\n".join(str(x) for x in g0["label_lines"]) + "\n", encoding="utf-8")
+    tok = tokenizer.FullTokenizer(vocab={str(t): i for i, t in enumerate(g0["vocab"])}, max_input_chars_per_word=100)
+    cfg = ModelConfig(LXMERT, n_layers=1, n_r_layers=1, n_x_layers=1, lq=23, nbox=10, vocab=len(g0["vocab"]))
+    fa = records.FeedAssembler(cfg, tok, records.load_label_map(str(tmp_path / "labels.txt")))
+    # everything of assemble() but the GPU box normalisation (tests/test_gpu_records.py covers that one)
+    orig = records.normalize_boxes
+    records.normalize_boxes = lambda b4, h, w, with_area, device=None: torch.from_numpy(
+        (b4.numpy().astype(np.float64) / np.stack([h.numpy(), w.numpy(), h.numpy(), w.numpy()], 1)[:, None, :]).astype(np.float32))
+    try:
+        feeds = fa.assemble(out)
+    finally:
+        records.normalize_boxes = orig
+    assert np.array_equal(feeds["query_ids"].numpy(), g["query_ids_padded"])
+    assert np.array_equal(feeds["query_mask"].numpy(), g["query_mask"])
+    assert np.array_equal(feeds["visn_mask"].numpy(), g["visn_mask"])
+    assert np.array_equal(feeds["boxes"].numpy(), g["boxes4_padded_f32"])
+    for i in range(len(lines)):
+        k = min(int(out["num_boxes"][i]), 10)
+        assert feeds["label_ids"][i, :k].tolist() == g[f"{i}_label_ids"][:k].tolist()
+        assert (out["product_id"][i], out["query_id"][i]) == tuple(g[f"{i}_ids"].tolist())
+
+
 def test_decode_edge_cases_and_errors():
     from kddcup_2020_multimodalitiesrecall_2nd_place_b200._lib import MmrError
     assert records.decode_lines([], pin=False)["queries"] == []

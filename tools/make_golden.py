@@ -336,9 +336,60 @@ if __name__ == "__main__" and "--ndcg" in sys.argv:
     ndcg_ref_cases()
     sys.exit(0)
 
+def records_kat_lxmert():
+    """The same lines through the LXMERT tree's OWN loader functions — read_line, seq_padding, seq_padding_2,
+    random_word (code/lxmert/src/utils.py:23-59, 61-96, 126-156; extracted by name: the module imports param, which
+    parses argv) — with the LXMERT tree's own BertTokenizer (100-character word limit)."""
+    import ast
+    import random
+    import tempfile
+    import types
+    g = np.load(os.path.join(OUT, "records_kat.npz"))
+    lines = [str(x) for x in g["lines"]]
+    label_map = {}
+    for ln in g["label_lines"]:
+        a = str(ln).split("\t")
+        label_map[a[0]] = a[1].replace(",", " ").replace(".", " ").replace("(", " ").replace(")", " ").strip()
+    sys.path.insert(0, os.path.join(REF, "code/lxmert/src"))
+    import importlib
+    lx = importlib.import_module("lxrt.tokenization")
+    src = open(os.path.join(REF, "code/lxmert/src/utils.py")).read()
+    tree = ast.parse(src)
+    want = ("read_line", "seq_padding", "seq_padding_2", "random_word", "random_query", "random_img")
+    fns = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in want]
+    assert len(fns) == len(want)
+    import base64
+    ns = {"np": np, "base64": base64, "random": random, "MAX_LABLETEXT_LENGTH": 8, "SHUFFLE_RATIO": 0.5,
+          "args": types.SimpleNamespace(shuffle_img=False, shuffle_query=False)}
+    exec(compile(ast.Module(body=fns, type_ignores=[]), "utils.py", "exec"), ns)
+    with tempfile.TemporaryDirectory() as d:
+        vf = os.path.join(d, "vocab.txt")
+        with open(vf, "w", encoding="utf-8") as f:
+            f.write("\n".join(str(t) for t in g["vocab"]) + "\n")
+        tok = lx.BertTokenizer(vf, do_lower_case=True)
+    random.seed(0)
+    out = {}
+    rec = [ns["read_line"](ln, label_map, tok) for ln in lines]
+    for i, r in enumerate(rec):
+        pid, boxes, feats, idx_labels, idx_labels_mask, idx_query, qid = r[:7]
+        out[f"{i}_boxes4_f64"] = np.asarray(boxes, np.float64)
+        out[f"{i}_label_ids"] = np.asarray(idx_labels, np.int64)
+        out[f"{i}_label_mask"] = np.asarray(idx_labels_mask, np.int64)
+        out[f"{i}_query_ids"] = np.asarray(idx_query, np.int64)
+        out[f"{i}_ids"] = np.array([pid, qid], np.int64)
+    pad_boxes, box_mask = ns["seq_padding_2"]([r[1] for r in rec], 10, 0)
+    out["boxes4_padded_f32"] = pad_boxes.astype(np.float32)
+    out["visn_mask"] = box_mask.astype(np.int64)
+    q_pad, q_mask = ns["seq_padding"]([r[5] for r in rec], 23, 0)
+    out["query_ids_padded"], out["query_mask"] = q_pad.astype(np.int64), q_mask.astype(np.int64)
+    np.savez_compressed(os.path.join(OUT, "records_kat_lxmert.npz"), **out)
+    print("records_kat_lxmert:", len(rec), "lines")
+
+
 if __name__ == "__main__" and "--records" in sys.argv:
     os.makedirs(OUT, exist_ok=True)
     records_kat()
+    records_kat_lxmert()
     sys.exit(0)
 
 if __name__ == "__main__" and "--tf-shim" in sys.argv:
