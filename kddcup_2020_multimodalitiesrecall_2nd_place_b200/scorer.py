@@ -152,6 +152,8 @@ class MatchScorer:
         g = self._graphs.get(key)
         if g is None:
             if key not in self._seen or len(self._graphs) >= 64:
+                if len(self._seen) > 4096:     # a caller that never reuses buffers: do not grow without bound
+                    self._seen.clear()
                 self._seen.add(key)            # first forward on these buffers: eager (also warms every lazy init)
                 launch()
                 return probs_out
