@@ -38,6 +38,15 @@ typedef enum {
 
 typedef enum { MMR_DT_FP16 = 0, MMR_DT_BF16 = 1 } mmr_dtype;
 
+/* Arithmetic of the model-level forward (mmr_config.precision).
+ *   MMR_PRECISION_FAST    every MMA operand rounded once to `dtype` (11 significand bits for fp16); fp32 accumulate,
+ *                         residual stream, LayerNorm, softmax.  Within 1e-3 of the fp32 reference on weights of the
+ *                         reference initialisers; up to 3e-3 on weights of trained magnitude.
+ *   MMR_PRECISION_STRICT  two-term split operands (x = hi + lo) on EVERY tensor-core GEMM, the three significant partial
+ *                         products accumulated in fp32 in one K-concatenated MMA chain; precise GELU / tanh; attention
+ *                         in fp32.  ~1e-5 of the fp32 reference on either weight set, at about a third of the throughput. */
+typedef enum { MMR_PRECISION_FAST = 0, MMR_PRECISION_STRICT = 1 } mmr_precision;
+
 typedef enum {
   MMR_ACT_NONE = 0,
   MMR_ACT_RELU = 1,      /* slim.conv2d default activation: imagebert_zk/model_triple.py:189,193 */
@@ -81,10 +90,17 @@ int mmr_abi_version(void);
  *                                                            of the batch (bit-identical to the per-box evaluation, 0) 
  *   MMR_TUNE_LX_MERGE      (env MMR_LX_MERGE,     default 1) LXMERT: the projections of the language and the visual
  *                                                            stream (different weights, one activation buffer) as ONE
- *                                                            launch each when batch x query length is a multiple of 256 */
+ *                                                            launch each when batch x query length is a multiple of 256
+ *   MMR_TUNE_PRUNE_LAST    (env MMR_PRUNE_LAST,   default 1) last encoder block: the scorers read sequence_output[:, 0]
+ *                                                            only (pixelbert.py:258-266, modeling.py:925), so keys / values
+ *                                                            are projected for all rows but attention, output projection,
+ *                                                            FFN and both LayerNorms run for the B [CLS] rows alone (LXMERT:
+ *                                                            the last cross layer's visual half, modeling.py:468-479, feeds
+ *                                                            nothing and is skipped); 0 = the full last block.  Forced off
+ *                                                            while mmr_set_debug_taps is non-zero (taps want every row). */
 enum { MMR_TUNE_GEMM_PAIR = 0, MMR_TUNE_GEMM_P16 = 1, MMR_TUNE_GEMM_TAIL = 2, MMR_TUNE_GEMM_CLUSTER = 3,
        MMR_TUNE_GEMM_LN = 4, MMR_TUNE_PDL = 5, MMR_TUNE_ATTN_TMA = 6, MMR_TUNE_ATTN_TC = 7, MMR_TUNE_LN_ROW_CFG = 8,
-       MMR_TUNE_LABEL_DEDUP = 9, MMR_TUNE_LX_MERGE = 10, MMR_TUNE_COUNT = 11 };
+       MMR_TUNE_LABEL_DEDUP = 9, MMR_TUNE_LX_MERGE = 10, MMR_TUNE_PRUNE_LAST = 11, MMR_TUNE_COUNT = 12 };
 mmr_status mmr_set_tuning(int knob, int value);
 /* Current value of a knob (-1 for an unknown one). */
 int mmr_get_tuning(int knob);
@@ -195,8 +211,30 @@ mmr_status mmr_attention(const void* q, int64_t ldq, const void* k, int64_t ldk,
                          const int32_t* key_mask, void* out16, int64_t ldo, int B, int Sq, int Sk,
                          int heads, int dtype, void* stream);
 
-/* fp32 -> 16-bit cast with 16-byte vector loads (region features [B*R,2048]). n must be a multiple of 8. */
+/* fp32 -> 16-bit cast with 16-byte vector loads (region features [B*R,2048]). n must be a multiple of 8.  fp16
+ * saturates at +-65504 instead of overflowing to inf (detector pool5 features are post-ReLU and far below that; a
+ * corrupt record must not poison a whole batch with NaNs). */
 mmr_status mmr_cast16(const float* x, void* out16, int64_t n, int dtype, void* stream);
+
+/* Attention for the FIRST query row of every pair only (the [CLS] row the poolers read: pixelbert.py:258-266,
+ * modeling.py:596-608): same arithmetic as mmr_attention, one CTA per pair.  q: 16-bit, the query row of pair b at
+ * q + b * q_pair_stride (elements); k / v: key row j of pair b at k + (b * Sk + j) * ldkv; out16 [B, ldo]. Sk <= 128. */
+mmr_status mmr_cls_attention(const void* q, int64_t q_pair_stride, const void* k, const void* v, int64_t ldkv,
+                             const int32_t* key_mask, void* out16, int64_t ldo, int B, int Sk, int heads, int dtype,
+                             void* stream);
+
+/* Strict-precision building blocks (MMR_PRECISION_STRICT).
+ * mmr_split3: out16[r] = [hi | lo | hi] (weights = 0) or [hi | hi | lo] (weights = 1) of act(x[r, :K]), hi = round16(x),
+ *   lo = round16(x - hi); `act` is applied in full precision first (tanhf / erff GELU).  A GEMM over the concatenated 3K
+ *   axis of an activation split and a weight split accumulates A_hi W_hi + A_lo W_hi + A_hi W_lo in fp32.
+ * mmr_attention_f32: the attention of pixelbert.py:790-850 / modeling.py:325-352 in fp32 on the CUDA cores; pair b has
+ *   its Sq query rows at q + b * q_pair + i * ldq, its Sk keys / values at k|v + b * kv_pair + j * ldkv, its output rows
+ *   at out + b * o_pair + i * ldo (all in elements); Sk <= 128. */
+mmr_status mmr_split3(const float* x, int64_t ldx, int rows, int K, void* out16, int64_t ldo, int act, int weights,
+                      int dtype, void* stream);
+mmr_status mmr_attention_f32(const float* q, int64_t q_pair, int64_t ldq, const float* k, const float* v, int64_t kv_pair,
+                             int64_t ldkv, const int32_t* key_mask, float* out, int64_t o_pair, int64_t ldo, int B,
+                             int Sq, int Sk, int heads, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Model level.
@@ -221,6 +259,7 @@ typedef struct {
   int32_t lq;           /* query tokens  (reference native: 20 zk/lds, 23 lxmert)                 */
   int32_t nbox;         /* region slots  (reference native: 10)                                   */
   int32_t max_batch;    /* workspace is sized for this many pairs per forward                     */
+  int32_t precision;    /* mmr_precision (ABI version 2)                                          */
 } mmr_config;
 
 /* One named fp32 host tensor, named exactly as in the reference checkpoint (TF variable name or torch
@@ -255,7 +294,12 @@ mmr_status mmr_create(const mmr_config* cfg, const mmr_tensor* weights, int n_we
                       mmr_handle** out);
 void mmr_destroy(mmr_handle* h);
 
-/* Scores B pairs (B <= max_batch).  probs_out dev fp32 [B,2] (softmax of the 2-way head; the reference
+/* Concurrency: a handle is not re-entrant, and the fused GEMM+LayerNorm kernel needs its whole grid co-resident, so
+ * at most ONE mmr_forward may be in flight per device.  Forwards of different handles issued on different streams of one
+ * device are serialised by the library (a cross-stream event wait) -- except while a stream is being captured into a
+ * CUDA graph, where the caller must keep replays of different handles' graphs from overlapping on one device.
+ *
+ * Scores B pairs (B <= max_batch).  probs_out dev fp32 [B,2] (softmax of the 2-way head; the reference
  * score is column 1 — for LXMERT column -1, same thing).  logits_out dev fp32 [B,2] or NULL: the pre-softmax
  * values (zk: 30 * margin-adjusted cosines, model_triple.py:81-85; lds: logits, run_pretraining_predict_score.py:
  * 491-492; lxmert: `logit`, the third return value of KDDModel.forward).  pooled_out dev fp32 [B,hidden] or NULL.
@@ -267,7 +311,9 @@ mmr_status mmr_forward(mmr_handle* h, const mmr_inputs* in, int B, float* probs_
 /* Debug / parity taps (BertModel.get_embedding_output / get_sequence_output, pixelbert.py:279-309): copies of
  * internal activations after the last forward (dev fp32, rows = pairs x tokens; LXMERT: all language rows, then all
  * visual rows).  which: 0 = embedding output, only kept when mmr_set_debug_taps(h, 1) was called before the forward
- * (one extra device copy per forward); 1 = final encoder layer output; 2 + i = output of encoder layer i
+ * (one extra device copy per forward); 1 = final encoder layer output, all rows -- also needs taps enabled before the
+ * forward, because the default forward computes the last block for the [CLS] rows only (MMR_TUNE_PRUNE_LAST);
+ * 2 + i = output of encoder layer i
  * (get_all_encoder_layers; single-stream models only), kept when mmr_set_debug_taps(h, 2) was called (allocates
  * n_layers x rows x hidden floats once, copies after every layer). */
 mmr_status mmr_set_debug_taps(mmr_handle* h, int enable);

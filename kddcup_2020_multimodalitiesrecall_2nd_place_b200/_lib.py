@@ -11,12 +11,13 @@ MMR_OK = 0
 DT_FP16, DT_BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_GELU_TANH, ACT_GELU_ERF, ACT_TANH = range(5)
 MODEL_ZK, MODEL_LDS, MODEL_LXMERT = range(3)
-TUNE_GEMM_PAIR, TUNE_GEMM_P16, TUNE_GEMM_TAIL, TUNE_GEMM_CLUSTER, TUNE_GEMM_LN, TUNE_PDL, TUNE_ATTN_TMA, TUNE_ATTN_TC, TUNE_LN_ROW_CFG, TUNE_LABEL_DEDUP, TUNE_LX_MERGE = range(11)
+TUNE_GEMM_PAIR, TUNE_GEMM_P16, TUNE_GEMM_TAIL, TUNE_GEMM_CLUSTER, TUNE_GEMM_LN, TUNE_PDL, TUNE_ATTN_TMA, TUNE_ATTN_TC, TUNE_LN_ROW_CFG, TUNE_LABEL_DEDUP, TUNE_LX_MERGE, TUNE_PRUNE_LAST = range(12)
+PRECISION_FAST, PRECISION_STRICT = 0, 1
 
 # every symbol include/mmrecall.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "mmr_last_error", "mmr_abi_version", "mmr_device_check", "mmr_set_tuning", "mmr_get_tuning", "mmr_tuning_generation",
-    "mmr_gemm", "mmr_gemm_layernorm", "mmr_gemm_layernorm_supported", "mmr_layernorm", "mmr_attention", "mmr_cast16", "mmr_am_softmax_head", "mmr_linear_head", "mmr_decode_tsv", "mmr_boxes_normalize", "mmr_ensemble_topk", "mmr_ndcg_at_k",
+    "mmr_gemm", "mmr_gemm_layernorm", "mmr_gemm_layernorm_supported", "mmr_layernorm", "mmr_attention", "mmr_cast16", "mmr_cls_attention", "mmr_split3", "mmr_attention_f32", "mmr_am_softmax_head", "mmr_linear_head", "mmr_decode_tsv", "mmr_boxes_normalize", "mmr_ensemble_topk", "mmr_ndcg_at_k",
     "mmr_create", "mmr_destroy", "mmr_forward", "mmr_set_debug_taps", "mmr_get_activation",
     "mmr_launches_per_forward", "mmr_set_profiling", "mmr_get_profile",
 ]
@@ -25,7 +26,7 @@ EXPORTS = [
 class MmrConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "model_kind", "dtype", "hidden", "heads", "intermediate", "vocab", "max_pos", "type_vocab", "feat_dim",
-        "label_len", "n_layers", "n_r_layers", "n_x_layers", "lq", "nbox", "max_batch")]
+        "label_len", "n_layers", "n_r_layers", "n_x_layers", "lq", "nbox", "max_batch", "precision")]
 
 
 class MmrTensor(C.Structure):
@@ -67,6 +68,9 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.mmr_layernorm.argtypes = [vp, i64, vp, vp, f32, i32, i32, vp, i64, vp, i64, f32, i32, i32, vp]
     lib.mmr_attention.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, i64, i32, i32, i32, i32, i32, vp]
     lib.mmr_cast16.argtypes = [vp, vp, i64, i32, vp]
+    lib.mmr_cls_attention.argtypes = [vp, i64, vp, vp, i64, vp, vp, i64, i32, i32, i32, i32, vp]
+    lib.mmr_split3.argtypes = [vp, i64, i32, i32, vp, i64, i32, i32, i32, vp]
+    lib.mmr_attention_f32.argtypes = [vp, i64, i64, vp, vp, i64, i64, vp, vp, i64, i64, i32, i32, i32, i32, vp]
     lib.mmr_gemm_layernorm.argtypes = [vp, i64, vp, i64, i32, i32, vp, vp, i64, vp, vp, f32, vp, i64, vp, i64, i32, vp]
     lib.mmr_gemm_layernorm_supported.argtypes = [i32, i32, i32]
     lib.mmr_set_tuning.argtypes = [i32, i32]

@@ -90,7 +90,7 @@ def run(sc: MatchScorer, feeds: Dict[str, torch.Tensor], pooled=False, logits=Fa
     if logits:
         out["logits"] = torch.empty((B, 2), dtype=torch.float32, device=dev)
     seq_chunks, emb_chunks, layer_chunks = [], [], []
-    sc.set_debug_taps(2 if all_layers else (1 if embedding else 0))
+    sc.set_debug_taps(2 if all_layers else (1 if (embedding or sequence) else 0))   # taps: every row of the last block
     for lo in range(0, B, sc.max_batch):
         hi = min(B, lo + sc.max_batch)
         chunk = {k: v[lo:hi].to(dev, non_blocking=True) for k, v in feeds.items()}

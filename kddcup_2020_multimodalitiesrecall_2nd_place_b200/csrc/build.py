@@ -17,7 +17,7 @@ HERE = Path(__file__).resolve().parent
 PKG = HERE.parent
 LIB = PKG / "libmmrecall.so"
 OBJ_DIR = HERE / "build"
-SOURCES = ["common.cu", "gemm_sm100.cu", "gemm2_sm100.cu", "gemm16_sm100.cu", "gemm_ln_sm100.cu", "gemm_lnrow_sm100.cu", "rowops.cu", "attention.cu", "attention_tc.cu", "attention_tc2.cu", "embed.cu", "ensemble.cu", "model.cu", "decode.cpp"]
+SOURCES = ["common.cu", "gemm_sm100.cu", "gemm2_sm100.cu", "gemm16_sm100.cu", "gemm_ln_sm100.cu", "gemm_lnrow_sm100.cu", "rowops.cu", "attention.cu", "attention_tc.cu", "attention_tc2.cu", "embed.cu", "cls_tail.cu", "strict.cu", "ensemble.cu", "model.cu", "decode.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -24,7 +24,7 @@ static bool g_tuning_init = false;
 static unsigned g_tuning_generation = 0;   // bumped by mmr_set_tuning: captured CUDA graphs of a forward are keyed on it
 static void tuning_init() {
   static const struct { const char* env; int def; } spec[MMR_TUNE_COUNT] = {
-      {"MMR_GEMM_PAIR", 1}, {"MMR_GEMM_P16", 1}, {"MMR_GEMM_TAIL", 1}, {"MMR_GEMM_CLUSTER", 1}, {"MMR_GEMM_LN", 1}, {"MMR_PDL", 1}, {"MMR_ATTN_TMA", 0}, {"MMR_ATTN_TC", 2}, {"MMR_LN_ROW_CFG", 0}, {"MMR_LABEL_DEDUP", 1}, {"MMR_LX_MERGE", 1}};
+      {"MMR_GEMM_PAIR", 1}, {"MMR_GEMM_P16", 1}, {"MMR_GEMM_TAIL", 1}, {"MMR_GEMM_CLUSTER", 1}, {"MMR_GEMM_LN", 1}, {"MMR_PDL", 1}, {"MMR_ATTN_TMA", 0}, {"MMR_ATTN_TC", 2}, {"MMR_LN_ROW_CFG", 0}, {"MMR_LABEL_DEDUP", 1}, {"MMR_LX_MERGE", 1}, {"MMR_PRUNE_LAST", 1}};
   for (int i = 0; i < MMR_TUNE_COUNT; ++i) {
     const char* e = getenv(spec[i].env);
     g_tuning[i] = e ? atoi(e) : spec[i].def;
@@ -64,7 +64,7 @@ mmr_status require_sm100() {
 }  // namespace mmr
 
 extern "C" const char* mmr_last_error(void) { return mmr::last_error_buf(); }
-extern "C" int mmr_abi_version(void) { return 1; }
+extern "C" int mmr_abi_version(void) { return 2; }
 extern "C" mmr_status mmr_set_tuning(int knob, int value) {
   if (knob < 0 || knob >= MMR_TUNE_COUNT) return mmr::fail(MMR_ERR_INVALID, "mmr_set_tuning: unknown knob %d", knob);
   if (!mmr::g_tuning_init) mmr::tuning_init();

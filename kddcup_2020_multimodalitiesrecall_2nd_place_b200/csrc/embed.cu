@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256)
 zk_region_sum_kernel(const float* __restrict__ feat32, const float* __restrict__ boxes5,
                      const int32_t* __restrict__ label_ids, const float* __restrict__ tables, int vocab,
                      const float* __restrict__ bc1, const float* __restrict__ Wb, const float* __restrict__ bb,
-                     typename E16::T* __restrict__ out16, int rows) {
+                     typename E16::T* __restrict__ out16, float* __restrict__ out32, int rows) {
   pdl_wait();
   pdl_launch_dependents();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -131,7 +131,7 @@ zk_region_sum_kernel(const float* __restrict__ feat32, const float* __restrict__
     row_load(wrow, Wb + d * kH, lane);
     row_axpy(out, bx, wrow);
   }
-  row_store<E16>(out, out16 + int64_t(row) * kH, nullptr, lane);
+  row_store<E16>(out, out16 ? out16 + int64_t(row) * kH : nullptr, out32 ? out32 + int64_t(row) * kH : nullptr, lane);
 }
 
 // ---- label term, computed once per DISTINCT label phrase of the batch
@@ -222,7 +222,8 @@ __global__ void __launch_bounds__(256)
 zk_region_sum_rep_kernel(const float* __restrict__ feat32, const float* __restrict__ boxes5,
                          const int32_t* __restrict__ rep, const float* __restrict__ term32,
                          const float* __restrict__ Wb, const float* __restrict__ bb,
-                         typename E16::T* __restrict__ out16, int rows, uint32_t* __restrict__ epoch_ptr) {
+                         typename E16::T* __restrict__ out16, float* __restrict__ out32, int rows,
+                         uint32_t* __restrict__ epoch_ptr) {
   pdl_wait();
   pdl_launch_dependents();
   if (blockIdx.x == 0 && threadIdx.x == 0) {   // claim and term kernels of this forward are complete (stream order)
@@ -245,7 +246,7 @@ zk_region_sum_rep_kernel(const float* __restrict__ feat32, const float* __restri
     row_load(wrow, Wb + d * kH, lane);
     row_axpy(out, bx, wrow);
   }
-  row_store<E16>(out, out16 + int64_t(row) * kH, nullptr, lane);
+  row_store<E16>(out, out16 ? out16 + int64_t(row) * kH : nullptr, out32 ? out32 + int64_t(row) * kH : nullptr, lane);
 }
 
 // X0 = LN(concat(E[q], region) + Ttype[seg] + Pos[[0..Lq-1] + [Lq]*R]); also emits the key mask
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(256)
 lx_label_z_kernel(const int32_t* __restrict__ label_ids, const float* __restrict__ E, const float* __restrict__ T,
                   const float* __restrict__ P, const float* __restrict__ gamma, const float* __restrict__ beta,
                   const float* __restrict__ wconv, const float* __restrict__ bconv, int rows,
-                  typename E16::T* __restrict__ z16) {
+                  typename E16::T* __restrict__ z16, float* __restrict__ z32) {
   pdl_wait();
   pdl_launch_dependents();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -374,7 +375,7 @@ lx_label_z_kernel(const int32_t* __restrict__ label_ids, const float* __restrict
     row_layernorm(x, gamma, beta, lane);
     row_axpy(z, __ldg(wconv + t), x);
   }
-  row_store<E16>(z, z16 + int64_t(row) * kH, nullptr, lane);
+  row_store<E16>(z, z16 ? z16 + int64_t(row) * kH : nullptr, z32 ? z32 + int64_t(row) * kH : nullptr, lane);
 }
 
 // acc32[row,:] += scale * LN_b(box4 . Wb^T + bb)   (modeling.py:524-525, 530); Wb is torch [768,4]
@@ -524,10 +525,10 @@ static inline int blocks_for(int rows) { return (rows + 7) / 8; }
 
 mmr_status zk_region_sum(const float* feat32, const float* boxes5, const int32_t* label_ids, const float* tables,
                          int vocab, const float* bc1, const float* Wb, const float* bb, void* out16, int rows,
-                         int dtype, cudaStream_t st) {
+                         int dtype, cudaStream_t st, float* out32) {
   MMR_DISPATCH16(dtype, ((void)launch_pdl(zk_region_sum_kernel<E16>, dim3(blocks_for(rows)), dim3(256), 0, st, 
                             feat32, boxes5, label_ids, tables, vocab, bc1, Wb, bb,
-                            static_cast<typename E16::T*>(out16), rows)));
+                            static_cast<typename E16::T*>(out16), out32, rows)));
   MMR_CUDA_OK(cudaGetLastError());
   return MMR_OK;
 }
@@ -545,9 +546,10 @@ mmr_status zk_label_terms(const int32_t* label_ids, const float* tables, int voc
 }
 mmr_status zk_region_sum_rep(const float* feat32, const float* boxes5, const int32_t* rep, const float* term32,
                              const float* Wb, const float* bb, void* out16, int rows, uint32_t* epoch_dev, int dtype,
-                             cudaStream_t st) {
+                             cudaStream_t st, float* out32) {
   MMR_DISPATCH16(dtype, ((void)launch_pdl(zk_region_sum_rep_kernel<E16>, dim3(blocks_for(rows)), dim3(256), 0, st,
-                            feat32, boxes5, rep, term32, Wb, bb, static_cast<typename E16::T*>(out16), rows, epoch_dev)));
+                            feat32, boxes5, rep, term32, Wb, bb, static_cast<typename E16::T*>(out16), out32, rows,
+                            epoch_dev)));
   MMR_CUDA_OK(cudaGetLastError());
   return MMR_OK;
 }
@@ -588,10 +590,10 @@ mmr_status lx_lang_embed(const int32_t* query_ids, const float* E, const float* 
 
 mmr_status lx_label_z(const int32_t* label_ids, const float* E, const float* T, const float* P,
                       const float* gamma, const float* beta, const float* wconv, const float* bconv, int rows,
-                      void* z16, int dtype, cudaStream_t st) {
+                      void* z16, int dtype, cudaStream_t st, float* z32) {
   MMR_DISPATCH16(dtype, ((void)launch_pdl(lx_label_z_kernel<E16>, dim3(blocks_for(rows)), dim3(256), 0, st, 
                             label_ids, E, T, P, gamma, beta, wconv, bconv, rows,
-                            static_cast<typename E16::T*>(z16))));
+                            static_cast<typename E16::T*>(z16), z32)));
   MMR_CUDA_OK(cudaGetLastError());
   return MMR_OK;
 }

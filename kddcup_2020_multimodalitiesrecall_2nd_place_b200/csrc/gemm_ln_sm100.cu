@@ -355,35 +355,26 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-// Exchange table + launch tag, one per device, grown on demand (mmr_create reserves it for max_batch so that no
-// allocation happens inside mmr_forward).  One fused GEMM+LN may be in flight per device at a time.
-struct LnWorkspace {
-  uint4* stats = nullptr;
-  uint32_t* epoch = nullptr;
-  int m_tiles = 0;
-};
-static LnWorkspace g_ln_ws[16];
+// Exchange table + launch tag.  The table belongs to whoever launches: every mmr_handle carves its own out of its
+// workspace arena at create time (model.cu), so two handles -- or graphs captured for them -- never share or outlive
+// one; the standalone operator (mmr_gemm_layernorm) takes a stream-ordered scratch allocation per call.  The kernel
+// still needs its whole grid co-resident: ONE fused GEMM+LN launch may run on a device at a time (mmr_forward
+// serialises forwards that arrive on different streams of one device, see model.cu).
 static unsigned long long* g_ln_trace = nullptr;
 
-mmr_status gemm_ln_reserve(int M) {
-  int dev = 0;
-  MMR_CUDA_OK(cudaGetDevice(&dev));
-  MMR_REQUIRE(dev >= 0 && dev < 16, "gemm_ln: device index %d out of range", dev);
-  LnWorkspace& ws = g_ln_ws[dev];
-  const int m_tiles = (M + kPairRows - 1) / kPairRows;
-  if (m_tiles <= ws.m_tiles) return MMR_OK;
-  MMR_CUDA_OK(cudaDeviceSynchronize());   // a kernel may still use the old table
-  if (ws.stats) cudaFree(ws.stats);
-  if (ws.epoch) cudaFree(ws.epoch);
-  ws = LnWorkspace();
-  const size_t bytes = size_t(m_tiles) * kLnSlots * kPairRows * sizeof(uint4);
-  MMR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&ws.stats), bytes));
-  MMR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&ws.epoch), 2 * sizeof(uint32_t)));
-  MMR_CUDA_OK(cudaMemset(ws.stats, 0, bytes));               // tag 0 = "never written"
-  const uint32_t init[2] = {1u, 0u};
-  MMR_CUDA_OK(cudaMemcpy(ws.epoch, init, sizeof(init), cudaMemcpyHostToDevice));
-  MMR_CUDA_OK(cudaDeviceSynchronize());
-  ws.m_tiles = m_tiles;
+size_t gemm_ln_table_bytes(int M) {
+  const size_t m_tiles = size_t((M + kPairRows - 1) / kPairRows);
+  return 256 + m_tiles * kLnSlots * kPairRows * sizeof(uint4);
+}
+mmr_status gemm_ln_table_init(void* mem, int M, LnTable* out, cudaStream_t stream) {
+  MMR_REQUIRE(mem != nullptr && out != nullptr && (reinterpret_cast<uintptr_t>(mem) & 255) == 0,
+              "gemm_ln: exchange table memory must be 256-byte aligned");
+  const size_t bytes = gemm_ln_table_bytes(M);
+  MMR_CUDA_OK(cudaMemsetAsync(mem, 0, bytes, stream));            // tag 0 = "never written"
+  MMR_CUDA_OK(cudaMemsetAsync(mem, 1, 1, stream));                // epoch[0] = 1 (little endian), epoch[1] = 0
+  out->epoch = static_cast<uint32_t*>(mem);
+  out->stats = static_cast<uint8_t*>(mem) + 256;
+  out->m_tiles = (M + kPairRows - 1) / kPairRows;
   return MMR_OK;
 }
 
@@ -448,7 +439,7 @@ static mmr_status launch_ln(const CUtensorMap& ta, const CUtensorMap& tw, const 
 mmr_status gemm_ln_2w(const void* A16, int64_t lda, const void* W16, const void* W16b, int64_t ldw, int M, int K,
                       const float* bias, const float* biasb, const float* residual, int64_t ldr, const float* gamma,
                       const float* gammab, const float* beta, const float* betab, int split_row, float eps, void* out16,
-                      int64_t ldo16, float* out32, int64_t ldo32, int dtype, cudaStream_t stream) {
+                      int64_t ldo16, float* out32, int64_t ldo32, int dtype, const LnTable& table, cudaStream_t stream) {
   MMR_TRY(require_sm100());
   const bool two = W16b != nullptr;
   MMR_REQUIRE(A16 && W16 && bias && residual && gamma && beta && out16 && out32, "gemm_ln: null argument");
@@ -467,9 +458,8 @@ mmr_status gemm_ln_2w(const void* A16, int64_t lda, const void* W16, const void*
   if (!two && (tuning(MMR_TUNE_GEMM_LN) == 2 || (tuning(MMR_TUNE_GEMM_LN) == 3 && K <= 1024)))
     return gemm_lnrow(A16, lda, W16, ldw, M, K, bias, residual, ldr, gamma, beta, eps, out16, ldo16, out32, ldo32, dtype,
                       stream);
-  MMR_TRY(gemm_ln_reserve(M));
-  int dev = 0;
-  MMR_CUDA_OK(cudaGetDevice(&dev));
+  MMR_REQUIRE(table.stats != nullptr && table.epoch != nullptr && (M + kPairRows - 1) / kPairRows <= table.m_tiles,
+              "gemm_ln: exchange table missing or too small for M=%d", M);
   const int ek = dtype == MMR_DT_BF16 ? 1 : 0;
   CUtensorMap ta, tw, tw2, tr, to32, to16;
   MMR_TRY(make_tmap_2d(&ta, A16, M, K, lda, kCtaRows, dtype));
@@ -478,17 +468,17 @@ mmr_status gemm_ln_2w(const void* A16, int64_t lda, const void* W16, const void*
   MMR_TRY(make_tmap_ex(&tr, residual, M, kLnN, ldr, 2, 32, 32, 128));
   MMR_TRY(make_tmap_ex(&to32, out32, M, kLnN, ldo32, 2, 32, 32, 128));
   MMR_TRY(make_tmap_ex(&to16, out16, M, kLnN, ldo16, ek, 32, 32, 64));
-  const LnWorkspace& ws = g_ln_ws[dev];
   GemmLnParams p{M, K, bias, gamma, beta, two ? biasb : bias, two ? gammab : gamma, two ? betab : beta,
-                 two ? split_row / kPairRows : 0x7fffffff, eps, ws.stats, ws.epoch, uint32_t(dtype), g_ln_trace};
+                 two ? split_row / kPairRows : 0x7fffffff, eps, static_cast<uint4*>(table.stats), table.epoch,
+                 uint32_t(dtype), g_ln_trace};
   if (dtype == MMR_DT_BF16) return launch_ln<BF16>(ta, tw, tw2, tr, to32, to16, p, stream);
   return launch_ln<FP16>(ta, tw, tw2, tr, to32, to16, p, stream);
 }
 mmr_status gemm_ln(const void* A16, int64_t lda, const void* W16, int64_t ldw, int M, int K, const float* bias,
                    const float* residual, int64_t ldr, const float* gamma, const float* beta, float eps, void* out16,
-                   int64_t ldo16, float* out32, int64_t ldo32, int dtype, cudaStream_t stream) {
+                   int64_t ldo16, float* out32, int64_t ldo32, int dtype, const LnTable& table, cudaStream_t stream) {
   return gemm_ln_2w(A16, lda, W16, nullptr, ldw, M, K, bias, nullptr, residual, ldr, gamma, nullptr, beta, nullptr, 0, eps,
-                    out16, ldo16, out32, ldo32, dtype, stream);
+                    out16, ldo16, out32, ldo32, dtype, table, stream);
 }
 
 }  // namespace mmr
@@ -497,8 +487,20 @@ extern "C" mmr_status mmr_gemm_layernorm(const void* A16, int64_t lda, const voi
                                          const float* bias, const float* residual, int64_t ldr, const float* gamma,
                                          const float* beta, float eps, void* out16, int64_t ldo16, float* out32,
                                          int64_t ldo32, int dtype, void* stream) {
-  return mmr::gemm_ln(A16, lda, W16, ldw, M, K, bias, residual, ldr, gamma, beta, eps, out16, ldo16, out32, ldo32,
-                      dtype, static_cast<cudaStream_t>(stream));
+  // per-call scratch table, stream-ordered: nothing is shared with any handle or any other call
+  using namespace mmr;
+  MMR_TRY(require_sm100());
+  MMR_REQUIRE(M > 0, "mmr_gemm_layernorm: M=%d", M);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  void* mem = nullptr;
+  MMR_CUDA_OK(cudaMallocAsync(&mem, gemm_ln_table_bytes(M), st));
+  LnTable table;
+  mmr_status rc = gemm_ln_table_init(mem, M, &table, st);
+  if (rc == MMR_OK)
+    rc = gemm_ln(A16, lda, W16, ldw, M, K, bias, residual, ldr, gamma, beta, eps, out16, ldo16, out32, ldo32, dtype,
+                 table, st);
+  cudaFreeAsync(mem, st);
+  return rc;
 }
 /* Debug only (not in the public header): device buffer of [grid][8 warps][4 tiles][8] uint64 phase stamps, or null. */
 extern "C" void mmr_debug_set_ln_trace(unsigned long long* dev_buf) { mmr::g_ln_trace = dev_buf; }

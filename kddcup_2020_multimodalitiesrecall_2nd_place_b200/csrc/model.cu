@@ -96,9 +96,9 @@ static mmr_status split16(const float* x, void* hi, void* lo, int64_t n, int dty
 
 // ------------------------------------------------------------------------------------------ handle
 struct Linear {
-  void* w16 = nullptr;   // [n, k] 16-bit
+  void* w16 = nullptr;   // [n, kw] 16-bit: kw = k (fast) or 3 k = [hi | hi | lo] (strict precision, strict.cu)
   float* bias = nullptr; // [n] or null
-  int n = 0, k = 0;
+  int n = 0, k = 0, kw = 0;
 };
 struct LNp {
   float* gamma = nullptr;
@@ -168,8 +168,19 @@ struct mmr_handle {
   float* lab_term32 = nullptr;
   float* layer_tap = nullptr;   // [n_layers, rows_max, hidden], allocated by mmr_set_debug_taps(h, 2)
   int32_t* key_mask = nullptr;
+  // [CLS]-row tail of the last block (MMR_TUNE_PRUNE_LAST): compact [B, .] buffers
+  void *xc16 = nullptr, *ctxc16 = nullptr, *hc16 = nullptr;
+  float* xc32 = nullptr;
+  // fused GEMM+LayerNorm row-statistics exchange table: this handle's own (gemm_ln_sm100.cu)
+  mmr::LnTable ln_table;
+  // strict precision (strict.cu): fp32 activations + ONE split-operand scratch reused by every GEMM
+  bool strict = false;
+  void* a16s = nullptr;          // [rows, 3 K] split A operand of the GEMM being launched
+  float *qkv32 = nullptr, *ctx32 = nullptr, *h32 = nullptr;
+  cudaEvent_t done_ev = nullptr; // recorded after every eager forward: cross-stream serialisation on one device
   int64_t rows_max = 0;   // encoder rows at max_batch
   int last_B = 0;
+  int pruned_last = 0;   // the last forward computed its final block for the [CLS] rows only
   int launches = 0;
   int keep_taps = 0;
   // per-launch event profiling (mmr_set_profiling / mmr_get_profile)
@@ -180,6 +191,49 @@ struct mmr_handle {
 };
 
 namespace mmr {
+
+// Makes `device` current for the lifetime of the object and restores the caller's device afterwards: no entry point of
+// this library leaves the calling thread on another device than it came with.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
+// At most one forward in flight per device (the fused GEMM+LayerNorm kernel needs its whole grid co-resident): the
+// last eager forward of every device leaves an event; a forward arriving on ANOTHER stream waits for it on the device.
+struct DeviceTail {
+  cudaEvent_t ev = nullptr;
+  cudaStream_t stream = nullptr;
+  const mmr_handle* owner = nullptr;
+};
+static DeviceTail g_tail[64];
+
+__global__ void transpose32_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
+  // dst [cols, rows] = src [rows, cols]^T
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? src[int64_t(r) * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) dst[int64_t(c) * rows + r] = tile[threadIdx.x][i];
+  }
+}
+static mmr_status transpose32(const float* src, float* dst, int rows, int cols, cudaStream_t st) {
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  transpose32_kernel<<<grid, block, 0, st>>>(src, dst, rows, cols);
+  MMR_CUDA_OK(cudaGetLastError());
+  return MMR_OK;
+}
 
 using TensorMap = std::map<std::string, const mmr_tensor*>;
 
@@ -195,6 +249,7 @@ struct Packer {
   float* staging;       // device fp32 staging for matrices
   size_t staging_floats;
   cudaStream_t st;
+  float* staging_t = nullptr;   // strict precision only: the fp32 [n, k] matrix after the TF-layout transpose
 
   mmr_status find(const std::string& name, int64_t want_numel, const mmr_tensor** out) const {
     auto it = tm.find(name);
@@ -222,15 +277,26 @@ struct Packer {
     MMR_TRY(find(name, int64_t(n) * k, &t));
     if (size_t(n) * k > staging_floats) return fail(MMR_ERR_INVALID, "staging too small for '%s'", name.c_str());
     MMR_CUDA_OK(cudaMemcpyAsync(staging, t->data, size_t(n) * k * 4, cudaMemcpyHostToDevice, st));
+    if (h->strict) {
+      // [n, 3k] = [hi | hi | lo] of the fp32 [n, k] matrix (the transpose of a TF kernel happens in fp32 first)
+      const float* src = staging;
+      if (tf_layout) {
+        MMR_TRY(transpose32(staging, staging_t, k, n, st));
+        src = staging_t;
+      }
+      return split3(src, k, n, k, dst16, 3 * int64_t(k), MMR_ACT_NONE, 1, h->cfg.dtype, st);
+    }
     MMR_TRY(pack16(staging, dst16, n, k, tf_layout, h->cfg.dtype, st));
     // staging is reused by the next call: the pageable H2D copy above is synchronous w.r.t. the host buffer but
     // the device-side order on `st` already serialises copy -> pack -> next copy.
     return MMR_OK;
   }
+  int kw_of(int k) const { return h->strict ? 3 * k : k; }
   mmr_status linear(const std::string& wname, const std::string& bname, int n, int k, bool tf_layout, Linear* L) {
     L->n = n;
     L->k = k;
-    L->w16 = h->weights.take(size_t(n) * k * 2);
+    L->kw = kw_of(k);
+    L->w16 = h->weights.take(size_t(n) * L->kw * 2);
     if (!L->w16) return fail(MMR_ERR_NOMEM, "weight arena exhausted at '%s'", wname.c_str());
     MMR_TRY(mat_into(wname, n, k, tf_layout, L->w16));
     if (!bname.empty()) MMR_TRY(f32(bname, n, &L->bias));
@@ -241,13 +307,14 @@ struct Packer {
     const int H = h->cfg.hidden;
     L->n = 3 * H;
     L->k = H;
-    L->w16 = h->weights.take(size_t(3) * H * H * 2);
+    L->kw = kw_of(H);
+    L->w16 = h->weights.take(size_t(3) * H * L->kw * 2);
     L->bias = static_cast<float*>(h->weights.take(size_t(3) * H * 4));
     if (!L->w16 || !L->bias) return fail(MMR_ERR_NOMEM, "weight arena exhausted at '%s'", prefix.c_str());
     const char* names[3] = {"query", "key", "value"};
     for (int i = 0; i < 3; ++i) {
       MMR_TRY(mat_into(prefix + names[i] + wsuffix, H, H, tf_layout,
-                       static_cast<uint8_t*>(L->w16) + size_t(i) * H * H * 2));
+                       static_cast<uint8_t*>(L->w16) + size_t(i) * H * L->kw * 2));
       const mmr_tensor* t;
       MMR_TRY(find(prefix + names[i] + bsuffix, H, &t));
       MMR_CUDA_OK(cudaMemcpyAsync(L->bias + i * H, t->data, size_t(H) * 4, cudaMemcpyHostToDevice, st));
@@ -289,36 +356,16 @@ static mmr_status pack_torch_ffn(Packer& pk, const std::string& in, const std::s
 
 static size_t weight_arena_bytes(const mmr_config& c) {
   const size_t H = c.hidden, I = c.intermediate, V = c.vocab;
-  const size_t att = 4 * H * H * 2 + 4 * H * 4 + 2 * H * 4 + 8 * 256;
-  const size_t ffn = 2 * H * I * 2 + (H + I) * 4 + 2 * H * 4 + 8 * 256;
+  const size_t e16 = c.precision == MMR_PRECISION_STRICT ? 6 : 2;   // bytes per stored matrix element
+  const size_t att = 4 * H * H * e16 + 4 * H * 4 + 2 * H * 4 + 8 * 256;
+  const size_t ffn = 2 * H * I * e16 + (H + I) * 4 + 2 * H * 4 + 8 * 256;
   size_t n = (V + c.max_pos + c.type_vocab + 2) * H * 4 + 16 * 256;
   n += size_t(c.n_layers + c.n_r_layers) * (att + ffn);
   n += size_t(c.n_x_layers) * (3 * att + 2 * ffn);
-  n += H * H * 2 + H * 4;  // pooler
-  n += size_t(c.feat_dim) * H * 2 + 2 * H * H * 2 + 64 * H * 4 + (1 << 20);  // projections, heads, small stuff
+  n += H * H * e16 + H * 4;  // pooler
+  n += size_t(c.feat_dim) * H * e16 + 2 * H * H * e16 + 64 * H * 4 + (1 << 20);  // projections, heads, small stuff
   if (c.model_kind == MMR_MODEL_IMAGEBERT_ZK) n += size_t(c.label_len) * V * H * 4;  // label tables
   return n;
-}
-
-__global__ void transpose32_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
-  // dst [cols, rows] = src [rows, cols]^T
-  __shared__ float tile[32][33];
-  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int r = r0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (r < rows && c < cols) ? src[int64_t(r) * cols + c] : 0.f;
-  }
-  __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int c = c0 + i, r = r0 + threadIdx.x;
-    if (r < rows && c < cols) dst[int64_t(c) * rows + r] = tile[threadIdx.x][i];
-  }
-}
-static mmr_status transpose32(const float* src, float* dst, int rows, int cols, cudaStream_t st) {
-  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
-  transpose32_kernel<<<grid, block, 0, st>>>(src, dst, rows, cols);
-  MMR_CUDA_OK(cudaGetLastError());
-  return MMR_OK;
 }
 
 // T_k = E . Wc1[k] in near-fp32 precision through three 16-bit GEMMs on split operands (create time only).
@@ -369,6 +416,10 @@ static mmr_status pack_weights(mmr_handle* h, const TensorMap& tm, cudaStream_t 
   float* staging = nullptr;
   MMR_CUDA_OK(cudaMalloc(&staging, staging_floats * 4));
   Packer pk{h, tm, staging, staging_floats, st};
+  if (h->strict && cudaMalloc(&pk.staging_t, staging_floats * 4) != cudaSuccess) {
+    cudaFree(staging);
+    return fail(MMR_ERR_NOMEM, "cannot allocate the strict-precision packing scratch");
+  }
   mmr_status rc = MMR_OK;
 #define PK(expr)                     \
   do {                               \
@@ -469,6 +520,7 @@ static mmr_status pack_weights(mmr_handle* h, const TensorMap& tm, cudaStream_t 
 done:
   cudaStreamSynchronize(st);
   cudaFree(staging);
+  if (pk.staging_t) cudaFree(pk.staging_t);
   return rc;
 }
 
@@ -479,63 +531,85 @@ static mmr_status alloc_workspace(mmr_handle* h) {
   if (c.model_kind == MMR_MODEL_IMAGEBERT_LDS) S = c.lq + 2 * c.nbox;
   const int64_t M = B * S;
   h->rows_max = M;
-  size_t bytes = 0;
-  auto add = [&](size_t n) { bytes += (n + 255) & ~size_t(255); };
-  add(B * R * c.feat_dim * 2);  // f16
-  add(B * R * H * 2);           // t16
-  add(B * R * H * 4);           // tmp32
-  add(M * H * 2);               // x16
-  add(M * H * 4);               // x32
-  add(M * 3 * H * 2);           // qkv16
-  add(M * H * 2);               // ctx16
-  add(M * I * 2);               // h16
-  add(M * 4);                   // key_mask
-  add(B * H * 2);               // pooled16
-  add(B * H * 4);               // pooled32
-  add(B * 2 * H * 4);           // head32
-  add(M * H * 4);               // emb_tap
+  const bool strict = h->strict;
+  const bool zk = c.model_kind == MMR_MODEL_IMAGEBERT_ZK;
   uint32_t lab_slots = 0;
-  if (c.model_kind == MMR_MODEL_IMAGEBERT_ZK) {
+  if (zk) {
     lab_slots = 1024;
     while (lab_slots < 4 * uint64_t(B * R)) lab_slots <<= 1;   // <= 25 % load
-    add(size_t(lab_slots) * 8);   // lab_tab
-    add(B * R * 4);               // lab_rep
-    add(B * R * H * 4);           // lab_term32
-    add(256);                     // lab_epoch_dev
   }
-  bytes += 4096;
-  MMR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->work.base), bytes));
-  h->work.cap = bytes;
-  h->f16 = h->work.take(B * R * c.feat_dim * 2);
-  h->t16 = h->work.take(B * R * H * 2);
-  h->tmp32 = static_cast<float*>(h->work.take(B * R * H * 4));
-  h->x16 = h->work.take(M * H * 2);
-  h->x32 = static_cast<float*>(h->work.take(M * H * 4));
-  h->qkv16 = h->work.take(M * 3 * H * 2);
-  h->ctx16 = h->work.take(M * H * 2);
-  h->h16 = h->work.take(M * I * 2);
-  h->key_mask = static_cast<int32_t*>(h->work.take(M * 4));
-  h->pooled16 = h->work.take(B * H * 2);
-  h->pooled32 = static_cast<float*>(h->work.take(B * H * 4));
-  h->head32 = static_cast<float*>(h->work.take(B * 2 * H * 4));
-  h->emb_tap = static_cast<float*>(h->work.take(M * H * 4));
-  if (!h->emb_tap) return fail(MMR_ERR_NOMEM, "workspace arena mis-sized");
-  if (lab_slots != 0) {
-    h->lab_tab = static_cast<unsigned long long*>(h->work.take(size_t(lab_slots) * 8));
-    h->lab_rep = static_cast<int32_t*>(h->work.take(B * R * 4));
-    h->lab_term32 = static_cast<float*>(h->work.take(B * R * H * 4));
-    h->lab_epoch_dev = static_cast<uint32_t*>(h->work.take(256));
-    if (!h->lab_term32 || !h->lab_epoch_dev) return fail(MMR_ERR_NOMEM, "workspace arena mis-sized (label terms)");
+  const size_t ln_bytes = gemm_ln_table_bytes(int(M));
+  // split A operand of the widest strict GEMM: FFN-out over all rows, or the 2048-d region projection
+  const size_t a16s_elems = size_t(std::max<int64_t>(M * 3 * I, B * R * 3 * int64_t(c.feat_dim)));
+  // One pass sizes the arena, a second hands out the pointers: the same list, so they cannot disagree.
+  for (int pass = 0; pass < 2; ++pass) {
+    size_t bytes = 0;
+    auto take = [&](size_t n) -> void* {
+      if (pass == 0) {
+        bytes += ((n + 255) & ~size_t(255));
+        return nullptr;
+      }
+      return h->work.take(n);
+    };
+    if (!strict) {
+      h->f16 = take(B * R * c.feat_dim * 2);
+      h->t16 = take(B * R * H * 2);
+      h->qkv16 = take(M * 3 * H * 2);
+      h->ctx16 = take(M * H * 2);
+      h->h16 = take(M * I * 2);
+      h->pooled16 = take(B * H * 2);
+      h->ctxc16 = take(B * H * 2);
+      h->hc16 = take(B * I * 2);
+    } else {
+      h->a16s = take(a16s_elems * 2);
+      h->qkv32 = static_cast<float*>(take(M * 3 * H * 4));
+      h->ctx32 = static_cast<float*>(take(M * H * 4));
+      h->h32 = static_cast<float*>(take(M * I * 4));
+    }
+    h->tmp32 = static_cast<float*>(take(B * R * H * 4));
+    h->x16 = take(M * H * 2);
+    h->x32 = static_cast<float*>(take(M * H * 4));
+    h->key_mask = static_cast<int32_t*>(take(M * 4));
+    h->pooled32 = static_cast<float*>(take(B * H * 4));
+    h->head32 = static_cast<float*>(take(B * 2 * H * 4));
+    h->emb_tap = static_cast<float*>(take(M * H * 4));
+    h->xc16 = take(B * H * 2);
+    h->xc32 = static_cast<float*>(take(B * H * 4));
+    void* ln_mem = take(ln_bytes);
+    if (zk) {
+      h->lab_tab = static_cast<unsigned long long*>(take(size_t(lab_slots) * 8));
+      h->lab_rep = static_cast<int32_t*>(take(B * R * 4));
+      h->lab_term32 = static_cast<float*>(take(B * R * H * 4));
+      h->lab_epoch_dev = static_cast<uint32_t*>(take(256));
+    }
+    if (pass == 0) {
+      bytes += 4096;
+      MMR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->work.base), bytes));
+      h->work.cap = bytes;
+      continue;
+    }
+    if (!h->xc32 || !ln_mem || (zk && !h->lab_epoch_dev)) return fail(MMR_ERR_NOMEM, "workspace arena mis-sized");
+    MMR_TRY(gemm_ln_table_init(ln_mem, int(M), &h->ln_table, nullptr));
+  }
+  if (zk) {
     h->lab_tab_mask = lab_slots - 1;
     MMR_CUDA_OK(cudaMemset(h->lab_tab, 0, size_t(lab_slots) * 8));   // epoch 0 = never written
     const uint32_t first_epoch = 1;
     MMR_CUDA_OK(cudaMemcpy(h->lab_epoch_dev, &first_epoch, sizeof(first_epoch), cudaMemcpyHostToDevice));
   }
+  MMR_CUDA_OK(cudaEventCreateWithFlags(&h->done_ev, cudaEventDisableTiming));
+  MMR_CUDA_OK(cudaDeviceSynchronize());
   return MMR_OK;
 }
 
 // ------------------------------------------------------------------------------------------ forward pieces
 enum LaunchKind { K_GEMM = 0, K_ATTENTION = 1, K_LAYERNORM = 2, K_ROW = 3 };
+
+// The last block only for the rows the pooler reads (include/mmrecall.h, MMR_TUNE_PRUNE_LAST); taps want every row.
+static bool prune_last(const mmr_handle* h) {
+  if (tuning(MMR_TUNE_PRUNE_LAST) == 0 || h->keep_taps != 0) return false;
+  return h->cfg.model_kind == MMR_MODEL_LXMERT ? !h->x_layers.empty() : !h->layers.empty();
+}
 
 struct Ctx {
   mmr_handle* h;
@@ -567,15 +641,22 @@ struct Ctx {
     MMR_TRY(gemm(A, lda, W.w16, W.k, M, W.n, W.k, W.bias, residual, H, out16, ldo16, out32, H, act, dt, st));
     return mark(K_GEMM, 2.0 * M * W.n * W.k);
   }
-  // x32[row0..] = LN(A . W^T + bias + x32[row0..]), x16 mirror: one fused kernel when the shape allows, else two.
-  mmr_status G_LN(const void* A, int64_t lda, const Linear& W, const LNp& ln, int64_t row0, int rows) {
+  // out = LN(A . W^T + bias + residual), fp32 rows + 16-bit mirror: one fused kernel when the shape allows, else two.
+  // residual (row stride ldr) may alias out32 (row stride H) — the residual stream updated in place — or be a strided
+  // view of it (the [CLS] rows feeding the compact tail buffers).
+  mmr_status G_LN_ex(const void* A, int64_t lda, const Linear& W, const LNp& ln, const float* residual, int64_t ldr,
+                     void* out16, float* out32, int rows) {
     if (gemm_ln_eligible(rows, W.n, W.k, dt)) {
-      MMR_TRY(gemm_ln(A, lda, W.w16, W.k, rows, W.k, W.bias, x32(row0), H, ln.gamma, ln.beta, 1e-12f, x16(row0), H,
-                      x32(row0), H, dt, st));
+      MMR_TRY(gemm_ln(A, lda, W.w16, W.k, rows, W.k, W.bias, residual, ldr, ln.gamma, ln.beta, 1e-12f, out16, H, out32, H,
+                      dt, h->ln_table, st));
       return mark(K_GEMM, 2.0 * rows * W.n * W.k);
     }
-    MMR_TRY(G(A, lda, W, rows, x32(row0), nullptr, 0, x32(row0), MMR_ACT_NONE));
-    return LN(x32(row0), ln, rows, x16(row0), x32(row0), 1.0f, 0);
+    MMR_TRY(gemm(A, lda, W.w16, W.k, rows, W.n, W.k, W.bias, residual, ldr, nullptr, 0, out32, H, MMR_ACT_NONE, dt, st));
+    MMR_TRY(mark(K_GEMM, 2.0 * rows * W.n * W.k));
+    return LN(out32, ln, rows, out16, out32, 1.0f, 0);
+  }
+  mmr_status G_LN(const void* A, int64_t lda, const Linear& W, const LNp& ln, int64_t row0, int rows) {
+    return G_LN_ex(A, lda, W, ln, x32(row0), H, x16(row0), x32(row0), rows);
   }
   // Two streams that share the activation buffers but not the weights (LXMERT: language rows [0, split), visual rows
   // [split, M)) run a projection as ONE launch when the split is a multiple of the 256-row tile: full waves instead
@@ -599,7 +680,7 @@ struct Ctx {
                    int rows, int split) {
     if (mergeable(W1, W2, split) && gemm_ln_eligible(rows, W1.n, W1.k, dt)) {
       MMR_TRY(gemm_ln_2w(A, lda, W1.w16, W2.w16, W1.k, rows, W1.k, W1.bias, W2.bias, x32(0), H, ln1.gamma, ln2.gamma,
-                         ln1.beta, ln2.beta, split, 1e-12f, x16(0), H, x32(0), H, dt, st));
+                         ln1.beta, ln2.beta, split, 1e-12f, x16(0), H, x32(0), H, dt, h->ln_table, st));
       return mark(K_GEMM, 2.0 * rows * W1.n * W1.k);
     }
     MMR_TRY(G_LN(A, lda, W1, ln1, 0, split));
@@ -657,9 +738,25 @@ static mmr_status two_stream_ffn(Ctx& c, const FfnBlock& F1, const FfnBlock& F2,
 }
 
 // first token of every pair: rows b*S of x16 (row stride S*H), pixelbert.py:258-266 / modeling.py:596-608
-static mmr_status pooler(Ctx& c, int B, int S) {
+static mmr_status pooler(Ctx& c, int B, int S, bool compact) {
   mmr_handle* h = c.h;
-  return c.G(h->x16, int64_t(S) * c.H, h->pooler, B, nullptr, h->pooled16, c.H, h->pooled32, MMR_ACT_TANH);
+  return c.G(compact ? h->xc16 : h->x16, compact ? int64_t(c.H) : int64_t(S) * c.H, h->pooler, B, nullptr, h->pooled16, c.H,
+             h->pooled32, MMR_ACT_TANH);
+}
+
+// The last block for the [CLS] rows only (MMR_TUNE_PRUNE_LAST; cls_tail.cu): the stream rows [row0, row0 + B*S) keep
+// their block INPUT, the B first rows leave through the compact xc16 / xc32 buffers.  Keys and values are projected
+// for every row (they feed the [CLS] query), everything after the attention runs on B rows.
+static mmr_status cls_tail_block(Ctx& c, const AttBlock& A, const FfnBlock& F, int64_t row0, int B, int S,
+                                 const int32_t* key_mask) {
+  mmr_handle* h = c.h;
+  MMR_TRY(qkv_proj(c, A.qkv, row0, B * S));
+  MMR_TRY(cls_attention(c.qkv(row0, 0), int64_t(S) * 3 * c.H, c.qkv(row0, 1), c.qkv(row0, 2), 3 * c.H, key_mask, h->ctxc16,
+                        c.H, B, S, h->cfg.heads, c.dt, c.st));
+  MMR_TRY(c.mark(K_ATTENTION, 4.0 * B * S * c.H));
+  MMR_TRY(c.G_LN_ex(h->ctxc16, c.H, A.out, A.ln, c.x32(row0), int64_t(S) * c.H, h->xc16, h->xc32, B));
+  MMR_TRY(c.G(h->xc16, c.H, F.in, B, nullptr, h->hc16, F.in.n, nullptr, h->act));
+  return c.G_LN_ex(h->hc16, F.in.n, F.out, F.ln, h->xc32, c.H, h->xc16, h->xc32, B);
 }
 
 static mmr_status forward_single_stream(Ctx& c, const mmr_inputs* in, int B, float* probs, float* logits) {
@@ -715,13 +812,18 @@ static mmr_status forward_single_stream(Ctx& c, const mmr_inputs* in, int B, flo
   }
   if (h->keep_taps)
     MMR_CUDA_OK(cudaMemcpyAsync(h->emb_tap, h->x32, size_t(B) * S * H * 4, cudaMemcpyDeviceToDevice, c.st));
+  const bool prune = prune_last(h);
   for (size_t i = 0; i < h->layers.size(); ++i) {
+    if (prune && i + 1 == h->layers.size()) {
+      MMR_TRY(cls_tail_block(c, h->layers[i].att, h->layers[i].ffn, 0, B, S, mask));
+      break;
+    }
     MMR_TRY(bert_layer(c, h->layers[i], 0, B, S, mask));
     if (h->layer_tap != nullptr && h->keep_taps >= 2)
       MMR_CUDA_OK(cudaMemcpyAsync(h->layer_tap + i * size_t(h->rows_max) * H, h->x32, size_t(B) * S * H * 4,
                                   cudaMemcpyDeviceToDevice, c.st));
   }
-  MMR_TRY(pooler(c, B, S));
+  MMR_TRY(pooler(c, B, S, prune));
   if (zk)
     MMR_TRY(zk_head(h->pooled32, h->am_wn, in->labels, B, probs, logits, c.st));
   else
@@ -766,10 +868,20 @@ static mmr_status forward_lxmert(Ctx& c, const mmr_inputs* in, int B, float* pro
   }
   for (size_t i = n_both; i < h->layers.size(); ++i) MMR_TRY(bert_layer(c, h->layers[i], 0, B, Lq, in->query_mask));
   for (size_t i = n_both; i < h->r_layers.size(); ++i) MMR_TRY(bert_layer(c, h->r_layers[i], v0, B, R, in->visn_mask));
-  for (const XLayer& X : h->x_layers) {                                                       // :589-591
+  const bool prune = prune_last(h);
+  for (size_t xi = 0; xi < h->x_layers.size(); ++xi) {                                        // :589-591
+    const XLayer& X = h->x_layers[xi];
     // cross attention both ways with ONE weight set, both from the pre-update streams (modeling.py:462-463)
     MMR_TRY(qkv_proj(c, X.cross.qkv, 0, nl + nv));
     MMR_TRY(attend(c, 0, Lq, v0, R, in->visn_mask, B));
+    if (prune && xi + 1 == h->x_layers.size()) {
+      // last cross layer: the pooler reads lang[:, 0] (modeling.py:925), so its visual half (cross attention into the
+      // visual stream, visual self-attention and FFN, modeling.py:468-479) feeds nothing; the language half needs the
+      // cross-attended language rows as keys / values of its self-attention, then only the [CLS] rows
+      MMR_TRY(out_proj_ln(c, X.cross, 0, nl));
+      MMR_TRY(cls_tail_block(c, X.lang_self, X.lang_ffn, 0, B, Lq, in->query_mask));
+      break;
+    }
     MMR_TRY(attend(c, v0, R, 0, Lq, in->query_mask, B));
     MMR_TRY(out_proj_ln(c, X.cross, 0, nl + nv));
     if (merge) {
@@ -782,11 +894,206 @@ static mmr_status forward_lxmert(Ctx& c, const mmr_inputs* in, int B, float* pro
       MMR_TRY(ffn_block(c, X.visn_ffn, v0, nv));
     }
   }
-  MMR_TRY(pooler(c, B, Lq));
+  MMR_TRY(pooler(c, B, Lq, prune));
   // logit_fc: Linear(768,1536) -> erf-GELU -> LayerNorm(1536) -> Linear(1536,2)  (kdd_model.py:167-172)
   MMR_TRY(gemm(h->pooled16, H, h->logit0.w16, H, B, 2 * H, H, h->logit0.bias, nullptr, 0, nullptr, 0, h->head32, 2 * H,
                MMR_ACT_GELU_ERF, c.dt, c.st));
   MMR_TRY(c.mark(K_GEMM, 2.0 * B * 2 * H * H));
+  MMR_TRY(linear_head(h->head32, 2 * H, h->logit_ln.gamma, h->logit_ln.beta, h->logit3_w, h->logit3_b, B, probs,
+                      logits, c.st));
+  return c.mark(K_ROW, 0);
+}
+
+
+// ------------------------------------------------------------------------------------------ strict precision
+// Same graphs as above with fp32 activations end to end and every tensor-core GEMM on two-term split operands
+// (strict.cu).  Built from plain pieces -- split, GEMM (+bias, +residual), two-pass LayerNorm, fp32 attention -- with
+// no fused GEMM+LN and no 16-bit activation buffer: this mode trades throughput for ~1e-5 agreement with the fp32
+// reference path and is meant to be easy to audit.
+struct SCtx {
+  mmr_handle* h;
+  cudaStream_t st;
+  int dt, H;
+  Ctx* book;   // launch bookkeeping (counts, profiling events)
+  // out32 = act_out(split(act_in(A32)) . W^T + bias) (+ residual)
+  mmr_status GS(const float* A32, int64_t lda, int rows, const Linear& W, int act_in, const float* residual, int64_t ldr,
+                float* out32, int64_t ldo, int act_out) {
+    MMR_TRY(split3(A32, lda, rows, W.k, h->a16s, 3 * int64_t(W.k), act_in, 0, dt, st));
+    MMR_TRY(book->mark(K_ROW, 0));
+    MMR_TRY(gemm(h->a16s, 3 * int64_t(W.k), W.w16, W.kw, rows, W.n, W.kw, W.bias, residual, ldr, nullptr, 0, out32, ldo,
+                 act_out, dt, st));
+    return book->mark(K_GEMM, 2.0 * rows * W.n * W.k);   // algorithmic FLOPs (the split triples the MMA work)
+  }
+  mmr_status LN(float* x, int64_t ldx, const LNp& p, int rows, float* out32, int64_t ldo, float scale, int accumulate) {
+    MMR_TRY(layernorm(x, ldx, p.gamma, p.beta, 1e-12f, rows, H, nullptr, 0, out32, ldo, scale, accumulate, dt, st));
+    return book->mark(K_LAYERNORM, 0.0);
+  }
+  // attention + output projection + LayerNorm, in place on x32 rows [row0, row0 + B*Sq); keys from [krow0, + B*Sk)
+  mmr_status att_block(const AttBlock& A, int64_t row0, int Sq, int64_t krow0, int Sk, const int32_t* key_mask, int B,
+                       bool project) {
+    const int64_t H3 = 3 * int64_t(H);
+    if (project) MMR_TRY(GS(h->x32 + row0 * H, H, B * Sq, A.qkv, MMR_ACT_NONE, nullptr, 0, h->qkv32 + row0 * H3, H3, MMR_ACT_NONE));
+    MMR_TRY(attention_f32(h->qkv32 + row0 * H3, Sq * H3, H3, h->qkv32 + krow0 * H3 + H, h->qkv32 + krow0 * H3 + 2 * H,
+                          Sk * H3, H3, key_mask, h->ctx32 + row0 * H, int64_t(Sq) * H, H, B, Sq, Sk, h->cfg.heads, st));
+    MMR_TRY(book->mark(K_ATTENTION, 4.0 * B * Sq * Sk * H));
+    return MMR_OK;
+  }
+  mmr_status out_ln(const AttBlock& A, int64_t row0, int rows) {
+    float* x = h->x32 + row0 * H;
+    MMR_TRY(GS(h->ctx32 + row0 * H, H, rows, A.out, MMR_ACT_NONE, x, H, x, H, MMR_ACT_NONE));
+    return LN(x, H, A.ln, rows, x, H, 1.0f, 0);
+  }
+  mmr_status ffn(const FfnBlock& F, int64_t row0, int rows, int act) {
+    float* x = h->x32 + row0 * H;
+    float* hb = h->h32 + row0 * F.in.n;
+    MMR_TRY(GS(x, H, rows, F.in, MMR_ACT_NONE, nullptr, 0, hb, F.in.n, MMR_ACT_NONE));
+    MMR_TRY(GS(hb, F.in.n, rows, F.out, act, x, H, x, H, MMR_ACT_NONE));   // GELU applied in fp32 while splitting
+    return LN(x, H, F.ln, rows, x, H, 1.0f, 0);
+  }
+  mmr_status self_layer(const AttBlock& A, const FfnBlock& F, int64_t row0, int B, int S, const int32_t* key_mask, int act) {
+    MMR_TRY(att_block(A, row0, S, row0, S, key_mask, B, true));
+    MMR_TRY(out_ln(A, row0, B * S));
+    return ffn(F, row0, B * S, act);
+  }
+  // last block for the [CLS] rows only: results land in xc32 [B, H]
+  mmr_status cls_tail(const AttBlock& A, const FfnBlock& F, int64_t row0, int B, int S, const int32_t* key_mask, int act) {
+    const int64_t H3 = 3 * int64_t(H);
+    MMR_TRY(GS(h->x32 + row0 * H, H, B * S, A.qkv, MMR_ACT_NONE, nullptr, 0, h->qkv32 + row0 * H3, H3, MMR_ACT_NONE));
+    // one query row per pair (stride S rows), compact context rows in ctx32 [B, H]
+    MMR_TRY(attention_f32(h->qkv32 + row0 * H3, S * H3, H3, h->qkv32 + row0 * H3 + H, h->qkv32 + row0 * H3 + 2 * H, S * H3,
+                          H3, key_mask, h->ctx32, H, H, B, 1, S, h->cfg.heads, st));
+    MMR_TRY(book->mark(K_ATTENTION, 4.0 * B * S * H));
+    MMR_TRY(GS(h->ctx32, H, B, A.out, MMR_ACT_NONE, h->x32 + row0 * H, int64_t(S) * H, h->xc32, H, MMR_ACT_NONE));
+    MMR_TRY(LN(h->xc32, H, A.ln, B, h->xc32, H, 1.0f, 0));
+    MMR_TRY(GS(h->xc32, H, B, F.in, MMR_ACT_NONE, nullptr, 0, h->h32, F.in.n, MMR_ACT_NONE));
+    MMR_TRY(GS(h->h32, F.in.n, B, F.out, act, h->xc32, H, h->xc32, H, MMR_ACT_NONE));
+    return LN(h->xc32, H, F.ln, B, h->xc32, H, 1.0f, 0);
+  }
+  mmr_status pool(int B, int S, bool compact) {
+    return GS(compact ? h->xc32 : h->x32, compact ? int64_t(H) : int64_t(S) * H, B, h->pooler, MMR_ACT_NONE, nullptr, 0,
+              h->pooled32, H, MMR_ACT_TANH);
+  }
+};
+
+static mmr_status forward_single_stream_strict(Ctx& c, const mmr_inputs* in, int B, float* probs, float* logits) {
+  mmr_handle* h = c.h;
+  const mmr_config& cfg = h->cfg;
+  const int H = c.H, R = cfg.nbox, Lq = cfg.lq;
+  const bool zk = cfg.model_kind == MMR_MODEL_IMAGEBERT_ZK;
+  const int S = zk ? Lq + R : Lq + 2 * R;
+  SCtx s{h, c.st, c.dt, H, &c};
+  const bool fused_in = zk && in->region_sum != nullptr;
+  MMR_REQUIRE(in->query_ids && in->segment_ids && (fused_in || (in->label_ids && in->feats)),
+              "mmr_forward: missing input pointer");
+  const int32_t* mask = nullptr;
+  if (zk) {
+    MMR_REQUIRE(in->len_query && in->num_boxes && in->labels && (fused_in || in->boxes),
+                "mmr_forward(zk): missing input pointer");
+    const float* region_sum = in->region_sum;
+    if (!fused_in) {
+      MMR_TRY(s.GS(in->feats, cfg.feat_dim, B * R, h->conv2, MMR_ACT_NONE, nullptr, 0, h->tmp32, H, MMR_ACT_RELU));
+      if ((reinterpret_cast<uintptr_t>(in->label_ids) & 15) == 0) {
+        MMR_TRY(zk_label_terms(in->label_ids, h->tables, cfg.vocab, h->bc1, h->lab_tab, h->lab_tab_mask, h->lab_epoch_dev,
+                               h->lab_rep, h->lab_term32, B * R, c.st));
+        MMR_TRY(c.mark(K_ROW, 0));
+        MMR_TRY(c.mark(K_ROW, 0));
+        MMR_TRY(zk_region_sum_rep(h->tmp32, in->boxes, h->lab_rep, h->lab_term32, h->Wb, h->bb, nullptr, B * R,
+                                  h->lab_epoch_dev, c.dt, c.st, h->ctx32));
+      } else {
+        MMR_TRY(zk_region_sum(h->tmp32, in->boxes, in->label_ids, h->tables, cfg.vocab, h->bc1, h->Wb, h->bb, nullptr, B * R,
+                              c.dt, c.st, h->ctx32));
+      }
+      MMR_TRY(c.mark(K_ROW, 0));
+      region_sum = h->ctx32;
+    }
+    MMR_TRY(s.GS(region_sum, H, B * R, h->featureemb, MMR_ACT_NONE, nullptr, 0, h->tmp32, H, MMR_ACT_NONE));
+    MMR_TRY(zk_embed(in->query_ids, in->segment_ids, h->tmp32, in->len_query, in->num_boxes, h->E, h->T, h->P,
+                     h->emb_ln.gamma, h->emb_ln.beta, Lq, R, B, h->x16, h->x32, h->key_mask, c.dt, c.st));
+    MMR_TRY(c.mark(K_ROW, 0));
+    mask = h->key_mask;
+  } else {
+    MMR_TRY(s.GS(in->feats, cfg.feat_dim, B * R, h->lds_feat, MMR_ACT_NONE, nullptr, 0, h->tmp32, H, MMR_ACT_NONE));
+    MMR_TRY(lds_embed(in->query_ids, in->segment_ids, in->label_ids, h->tmp32, h->E, h->T, h->P, h->emb_ln.gamma,
+                      h->emb_ln.beta, h->wl, Lq, R, B, h->x16, h->x32, c.dt, c.st));
+    MMR_TRY(c.mark(K_ROW, 0));
+  }
+  if (h->keep_taps)
+    MMR_CUDA_OK(cudaMemcpyAsync(h->emb_tap, h->x32, size_t(B) * S * H * 4, cudaMemcpyDeviceToDevice, c.st));
+  const bool prune = prune_last(h);
+  for (size_t i = 0; i < h->layers.size(); ++i) {
+    const Layer& L = h->layers[i];
+    if (prune && i + 1 == h->layers.size()) {
+      MMR_TRY(s.cls_tail(L.att, L.ffn, 0, B, S, mask, h->act));
+      break;
+    }
+    MMR_TRY(s.self_layer(L.att, L.ffn, 0, B, S, mask, h->act));
+    if (h->layer_tap != nullptr && h->keep_taps >= 2)
+      MMR_CUDA_OK(cudaMemcpyAsync(h->layer_tap + i * size_t(h->rows_max) * H, h->x32, size_t(B) * S * H * 4,
+                                  cudaMemcpyDeviceToDevice, c.st));
+  }
+  MMR_TRY(s.pool(B, S, prune));
+  if (zk)
+    MMR_TRY(zk_head(h->pooled32, h->am_wn, in->labels, B, probs, logits, c.st));
+  else
+    MMR_TRY(linear_head(h->pooled32, H, nullptr, nullptr, h->cls_w, h->cls_b, B, probs, logits, c.st));
+  return c.mark(K_ROW, 0);
+}
+
+static mmr_status forward_lxmert_strict(Ctx& c, const mmr_inputs* in, int B, float* probs, float* logits) {
+  mmr_handle* h = c.h;
+  const mmr_config& cfg = h->cfg;
+  const int H = c.H, R = cfg.nbox, Lq = cfg.lq;
+  SCtx s{h, c.st, c.dt, H, &c};
+  MMR_REQUIRE(in->query_ids && in->label_ids && in->feats && in->boxes && in->query_mask && in->visn_mask,
+              "mmr_forward(lxmert): missing input pointer");
+  const int64_t v0 = int64_t(B) * Lq;
+  const int nl = B * Lq, nv = B * R;
+  const int act = h->act;
+  MMR_TRY(lx_lang_embed(in->query_ids, h->E, h->T, h->P, h->emb_ln.gamma, h->emb_ln.beta, Lq, B, c.x16(0), c.x32(0),
+                        c.dt, c.st));
+  MMR_TRY(c.mark(K_ROW, 0));
+  const float third = 1.0f / 3.0f;
+  float* xv = c.x32(v0);
+  MMR_TRY(s.GS(in->feats, cfg.feat_dim, nv, h->visn_fc, MMR_ACT_NONE, nullptr, 0, h->tmp32, H, MMR_ACT_NONE));
+  MMR_TRY(s.LN(h->tmp32, H, h->visn_ln, nv, xv, H, third, 0));
+  MMR_TRY(lx_box_ln(in->boxes, h->box_w, h->box_b, h->box_ln.gamma, h->box_ln.beta, third, nv, xv, c.st));
+  MMR_TRY(c.mark(K_ROW, 0));
+  MMR_TRY(lx_label_z(in->label_ids, h->E, h->T, h->P, h->emb_ln.gamma, h->emb_ln.beta, h->wconv, h->bconv, nv, nullptr,
+                     c.dt, c.st, h->ctx32));
+  MMR_TRY(c.mark(K_ROW, 0));
+  MMR_TRY(s.GS(h->ctx32, H, nv, h->label_fc, MMR_ACT_NONE, nullptr, 0, h->tmp32, H, MMR_ACT_NONE));
+  MMR_TRY(s.LN(h->tmp32, H, h->label_ln, nv, xv, H, third, 1));
+  if (h->keep_taps)
+    MMR_CUDA_OK(cudaMemcpyAsync(h->emb_tap, h->x32, size_t(nl + nv) * H * 4, cudaMemcpyDeviceToDevice, c.st));
+  for (const Layer& L : h->layers) MMR_TRY(s.self_layer(L.att, L.ffn, 0, B, Lq, in->query_mask, act));
+  for (const Layer& L : h->r_layers) MMR_TRY(s.self_layer(L.att, L.ffn, v0, B, R, in->visn_mask, act));
+  const bool prune = prune_last(h);
+  for (size_t xi = 0; xi < h->x_layers.size(); ++xi) {
+    const XLayer& X = h->x_layers[xi];
+    const bool last = prune && xi + 1 == h->x_layers.size();
+    // one projection of both streams with the shared cross-attention weights, then attention each way from the
+    // pre-update streams (modeling.py:462-463)
+    MMR_TRY(s.GS(h->x32, H, nl + nv, X.cross.qkv, MMR_ACT_NONE, nullptr, 0, h->qkv32, 3 * int64_t(H), MMR_ACT_NONE));
+    MMR_TRY(s.att_block(X.cross, 0, Lq, v0, R, in->visn_mask, B, false));
+    if (last) {
+      MMR_TRY(s.out_ln(X.cross, 0, nl));
+      MMR_TRY(s.cls_tail(X.lang_self, X.lang_ffn, 0, B, Lq, in->query_mask, act));
+      break;
+    }
+    MMR_TRY(s.att_block(X.cross, v0, R, 0, Lq, in->query_mask, B, false));
+    MMR_TRY(s.out_ln(X.cross, 0, nl + nv));
+    MMR_TRY(s.att_block(X.lang_self, 0, Lq, 0, Lq, in->query_mask, B, true));
+    MMR_TRY(s.out_ln(X.lang_self, 0, nl));
+    MMR_TRY(s.att_block(X.visn_self, v0, R, v0, R, in->visn_mask, B, true));
+    MMR_TRY(s.out_ln(X.visn_self, v0, nv));
+    MMR_TRY(s.ffn(X.lang_ffn, 0, nl, act));
+    MMR_TRY(s.ffn(X.visn_ffn, v0, nv, act));
+  }
+  MMR_TRY(s.pool(B, Lq, prune));
+  // logit_fc: Linear(768,1536) -> erf-GELU -> LayerNorm(1536) -> Linear(1536,2)  (kdd_model.py:167-172)
+  MMR_TRY(s.GS(h->pooled32, H, B, h->logit0, MMR_ACT_NONE, nullptr, 0, h->head32, 2 * int64_t(H), MMR_ACT_NONE));
+  MMR_TRY(act32(h->head32, int64_t(B) * 2 * H, MMR_ACT_GELU_ERF, c.st));
+  MMR_TRY(c.mark(K_ROW, 0));
   MMR_TRY(linear_head(h->head32, 2 * H, h->logit_ln.gamma, h->logit_ln.beta, h->logit3_w, h->logit3_b, B, probs,
                       logits, c.st));
   return c.mark(K_ROW, 0);
@@ -801,7 +1108,10 @@ extern "C" mmr_status mmr_create(const mmr_config* cfg, const mmr_tensor* weight
   MMR_REQUIRE(cfg && weights && out && n_weights > 0, "mmr_create: null argument");
   *out = nullptr;
   MMR_TRY(mmr_device_check(device));
-  MMR_CUDA_OK(cudaSetDevice(device));
+  MMR_REQUIRE(device >= 0 && device < 64, "mmr_create: device index %d out of range", device);
+  DeviceGuard guard(device);
+  MMR_REQUIRE(cfg->precision == MMR_PRECISION_FAST || cfg->precision == MMR_PRECISION_STRICT,
+              "mmr_create: bad precision %d", cfg->precision);
   MMR_REQUIRE(cfg->hidden == 768 && cfg->heads == 12, "mmr_create: only hidden=768 / heads=12 (bert_config.json) is built");
   MMR_REQUIRE(cfg->intermediate % 64 == 0 && cfg->intermediate % 16 == 0, "mmr_create: intermediate must be a multiple of 64");
   MMR_REQUIRE(cfg->feat_dim % 64 == 0, "mmr_create: feat_dim must be a multiple of 64");
@@ -819,6 +1129,7 @@ extern "C" mmr_status mmr_create(const mmr_config* cfg, const mmr_tensor* weight
   mmr_handle* h = new mmr_handle();
   h->cfg = *cfg;
   h->device = device;
+  h->strict = cfg->precision == MMR_PRECISION_STRICT;
   TensorMap tm;
   for (int i = 0; i < n_weights; ++i)
     if (weights[i].name) tm[weights[i].name] = &weights[i];
@@ -837,8 +1148,6 @@ extern "C" mmr_status mmr_create(const mmr_config* cfg, const mmr_tensor* weight
     }
   }
   if (rc == MMR_OK) rc = alloc_workspace(h);
-  if (rc == MMR_OK && gemm_ln_eligible(int(h->rows_max), cfg->hidden, cfg->hidden, cfg->dtype))
-    rc = gemm_ln_reserve(int(h->rows_max));
   if (rc != MMR_OK) {
     mmr_destroy(h);
     return rc;
@@ -849,7 +1158,10 @@ extern "C" mmr_status mmr_create(const mmr_config* cfg, const mmr_tensor* weight
 
 extern "C" void mmr_destroy(mmr_handle* h) {
   if (!h) return;
-  cudaSetDevice(h->device);
+  mmr::DeviceGuard guard(h->device);
+  cudaDeviceSynchronize();   // nothing of this handle may still run when its arenas (and exchange table) go away
+  if (h->device >= 0 && h->device < 64 && mmr::g_tail[h->device].owner == h) mmr::g_tail[h->device] = mmr::DeviceTail();
+  if (h->done_ev) cudaEventDestroy(h->done_ev);
   if (h->weights.base) cudaFree(h->weights.base);
   if (h->work.base) cudaFree(h->work.base);
   if (h->layer_tap) cudaFree(h->layer_tap);
@@ -862,19 +1174,38 @@ extern "C" mmr_status mmr_forward(mmr_handle* h, const mmr_inputs* in, int B, fl
   using namespace mmr;
   MMR_REQUIRE(h && in && probs_out, "mmr_forward: null argument");
   MMR_REQUIRE(B > 0 && B <= h->cfg.max_batch, "mmr_forward: B=%d outside (0, max_batch=%d]", B, h->cfg.max_batch);
+  DeviceGuard guard(h->device);
   MMR_TRY(require_sm100());
   Ctx c{h, static_cast<cudaStream_t>(stream), h->cfg.dtype, h->cfg.hidden};
+  // one forward in flight per device: wait (on the device) for the previous eager forward if it went to another stream
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  MMR_CUDA_OK(cudaStreamIsCapturing(c.st, &cap));
+  const bool eager = cap == cudaStreamCaptureStatusNone;
+  DeviceTail& tail = g_tail[h->device];
+  if (eager && tail.ev != nullptr && tail.stream != c.st) MMR_CUDA_OK(cudaStreamWaitEvent(c.st, tail.ev, 0));
   if (h->prof_on) {
     h->prof_n = 0;
     MMR_CUDA_OK(cudaEventRecord(h->prof_ev[0], c.st));
   }
-  mmr_status rc = h->cfg.model_kind == MMR_MODEL_LXMERT ? forward_lxmert(c, in, B, probs_out, logits_out)
-                                                        : forward_single_stream(c, in, B, probs_out, logits_out);
+  mmr_status rc;
+  if (h->strict)
+    rc = h->cfg.model_kind == MMR_MODEL_LXMERT ? forward_lxmert_strict(c, in, B, probs_out, logits_out)
+                                               : forward_single_stream_strict(c, in, B, probs_out, logits_out);
+  else
+    rc = h->cfg.model_kind == MMR_MODEL_LXMERT ? forward_lxmert(c, in, B, probs_out, logits_out)
+                                               : forward_single_stream(c, in, B, probs_out, logits_out);
   if (rc != MMR_OK) return rc;
   if (pooled_out != nullptr)
     MMR_CUDA_OK(cudaMemcpyAsync(pooled_out, h->pooled32, size_t(B) * h->cfg.hidden * 4, cudaMemcpyDeviceToDevice,
                                 c.st));
+  if (eager) {
+    MMR_CUDA_OK(cudaEventRecord(h->done_ev, c.st));
+    tail.ev = h->done_ev;
+    tail.stream = c.st;
+    tail.owner = h;
+  }
   h->last_B = B;
+  h->pruned_last = prune_last(h) ? 1 : 0;
   h->launches = c.launches;
   return MMR_OK;
 }
@@ -884,7 +1215,7 @@ extern "C" mmr_status mmr_set_debug_taps(mmr_handle* h, int enable) {
   MMR_REQUIRE(enable >= 0 && enable <= 2, "mmr_set_debug_taps: enable must be 0, 1 or 2");
   if (enable == 2 && h->layer_tap == nullptr) {
     MMR_REQUIRE(h->cfg.model_kind != MMR_MODEL_LXMERT, "mmr_set_debug_taps: per-layer taps are for single-stream models");
-    MMR_CUDA_OK(cudaSetDevice(h->device));
+    mmr::DeviceGuard guard(h->device);
     MMR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->layer_tap),
                            h->layers.size() * size_t(h->rows_max) * h->cfg.hidden * 4));
   }
@@ -897,9 +1228,10 @@ extern "C" mmr_status mmr_get_activation(mmr_handle* h, int which, float* dst, i
   MMR_REQUIRE(h && dst, "mmr_get_activation: null argument");
   MMR_REQUIRE(h->last_B > 0, "mmr_get_activation: no forward has run yet");
   const mmr_config& c = h->cfg;
-  int64_t S = c.lq + c.nbox;
-  if (c.model_kind == MMR_MODEL_IMAGEBERT_LDS) S = c.lq + 2 * c.nbox;
-  const int64_t have = int64_t(h->last_B) * S * c.hidden;
+  DeviceGuard guard(h->device);
+  // bounded by the workspace, not by the last eager batch: a forward replayed from a CUDA graph does not pass through
+  // mmr_forward, so the host cannot know its batch
+  const int64_t have = h->rows_max * c.hidden;
   MMR_REQUIRE(n_floats > 0 && n_floats <= have, "mmr_get_activation: n_floats=%lld exceeds %lld", (long long)n_floats,
               (long long)have);
   const float* src = nullptr;
@@ -907,6 +1239,9 @@ extern "C" mmr_status mmr_get_activation(mmr_handle* h, int which, float* dst, i
     MMR_REQUIRE(h->keep_taps, "mmr_get_activation: embedding tap needs mmr_set_debug_taps(h, 1) before the forward");
     src = h->emb_tap;
   } else if (which == 1) {
+    MMR_REQUIRE(h->keep_taps || !h->pruned_last,
+                "mmr_get_activation: the final-layer tap needs mmr_set_debug_taps(h, 1) before the forward (the default "
+                "forward computes the last block for the [CLS] rows only)");
     src = h->x32;
   } else if (which >= 2 && which < 2 + int(h->layers.size()) && c.model_kind != MMR_MODEL_LXMERT) {
     MMR_REQUIRE(h->keep_taps >= 2 && h->layer_tap, "mmr_get_activation: layer taps need mmr_set_debug_taps(h, 2)");

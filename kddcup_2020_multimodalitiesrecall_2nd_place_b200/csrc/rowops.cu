@@ -78,8 +78,15 @@ cast16_kernel(const float4* __restrict__ x, uint4* __restrict__ out, int64_t n8)
   int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
   for (; i < n8; i += stride) {
-    const float4 a = __ldcs(x + 2 * i);      // streaming: features are read exactly once
-    const float4 b = __ldcs(x + 2 * i + 1);
+    float4 a = __ldcs(x + 2 * i);      // streaming: features are read exactly once
+    float4 b = __ldcs(x + 2 * i + 1);
+    if constexpr (E16::kFmt == MMR_DT_FP16) {   // saturate instead of overflowing to inf (NaN stays NaN)
+      constexpr float kMax = 65504.0f;
+      a.x = fminf(fmaxf(a.x, -kMax), kMax); a.y = fminf(fmaxf(a.y, -kMax), kMax);
+      a.z = fminf(fmaxf(a.z, -kMax), kMax); a.w = fminf(fmaxf(a.w, -kMax), kMax);
+      b.x = fminf(fmaxf(b.x, -kMax), kMax); b.y = fminf(fmaxf(b.y, -kMax), kMax);
+      b.z = fminf(fmaxf(b.z, -kMax), kMax); b.w = fminf(fmaxf(b.w, -kMax), kMax);
+    }
     uint4 o;
     o.x = E16::pack(a.x, a.y);
     o.y = E16::pack(a.z, a.w);

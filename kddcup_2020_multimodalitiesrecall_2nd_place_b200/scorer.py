@@ -54,18 +54,25 @@ class MatchScorer:
     """One model (zk / lds / lxmert) resident on one B200."""
 
     def __init__(self, cfg: ModelConfig, weights: Dict[str, np.ndarray], device: int = 0, dtype: str = "fp16",
-                 max_batch: int = 256):
+                 max_batch: int = 256, precision: str = "fast"):
+        """precision: "fast" = every MMA operand rounded once to `dtype`; "strict" = two-term split operands on every
+        GEMM, precise activations, fp32 attention (~1e-5 of the fp32 reference path at about a third of the
+        throughput; include/mmrecall.h, mmr_precision)."""
         self.lib = _lib.load()
         self.cfg = cfg
         self.device = torch.device("cuda", device)
         self.max_batch = int(max_batch)
         self.dtype = dtype
+        if precision not in ("fast", "strict"):
+            raise ValueError(f"precision must be 'fast' or 'strict', got {precision!r}")
+        self.precision = precision
         _lib.check(self.lib.mmr_device_check(device))
         c = _lib.MmrConfig(
             model_kind=KIND_CODE[cfg.kind], dtype=_DT[dtype], hidden=cfg.hidden, heads=cfg.heads,
             intermediate=cfg.intermediate, vocab=cfg.vocab, max_pos=cfg.max_pos, type_vocab=cfg.type_vocab,
             feat_dim=cfg.feat_dim, label_len=cfg.label_len, n_layers=cfg.n_layers, n_r_layers=cfg.n_r_layers,
-            n_x_layers=cfg.n_x_layers, lq=cfg.lq, nbox=cfg.nbox, max_batch=self.max_batch)
+            n_x_layers=cfg.n_x_layers, lq=cfg.lq, nbox=cfg.nbox, max_batch=self.max_batch,
+            precision=_lib.PRECISION_STRICT if precision == "strict" else _lib.PRECISION_FAST)
         keep = []
         arr = (_lib.MmrTensor * len(weights))()
         for i, (name, w) in enumerate(weights.items()):

@@ -25,11 +25,11 @@ def test_library_loads_and_exports_every_declared_symbol():
     lib = _lib.load(build_if_missing=True)
     for name in _declared_symbols():
         assert hasattr(lib, name), f"libmmrecall.so does not export {name}"
-    assert lib.mmr_abi_version() == 1
+    assert lib.mmr_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
-    assert ctypes.sizeof(_lib.MmrConfig) == 16 * 4
+    assert ctypes.sizeof(_lib.MmrConfig) == 17 * 4
     assert ctypes.sizeof(_lib.MmrInputs) == 11 * ctypes.sizeof(ctypes.c_void_p)
     assert ctypes.sizeof(_lib.MmrTensor) == 8 + 8 + 8 + 4 * 8   # name, data, ndim (+pad), dims[4]
 
