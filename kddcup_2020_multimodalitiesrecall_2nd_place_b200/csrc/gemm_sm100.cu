@@ -262,7 +262,7 @@ static mmr_status dispatch_act(int act, const CUtensorMap& ta, const CUtensorMap
 
 mmr_status gemm(const void* A16, int64_t lda, const void* W16, int64_t ldw, int M, int N, int K,
                 const float* bias, const float* residual, int64_t ldr, void* out16, int64_t ldo16,
-                float* out32, int64_t ldo32, int act, int dtype, cudaStream_t stream) {
+                float* out32, int64_t ldo32, int act, int dtype, cudaStream_t stream, bool single_cta_only) {
   MMR_TRY(require_sm100());
   MMR_REQUIRE(A16 && W16, "mmr_gemm: null operand");
   MMR_REQUIRE(out16 || out32, "mmr_gemm: no output given");
@@ -281,7 +281,7 @@ mmr_status gemm(const void* A16, int64_t lda, const void* W16, int64_t ldw, int 
   MMR_REQUIRE(!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "mmr_gemm: bias must be 16-byte aligned");
   MMR_REQUIRE(dtype == MMR_DT_BF16 || dtype == MMR_DT_FP16, "mmr_gemm: bad dtype %d", dtype);
 
-  const bool pair_enabled = tuning(MMR_TUNE_GEMM_PAIR) != 0;
+  const bool pair_enabled = tuning(MMR_TUNE_GEMM_PAIR) != 0 && !single_cta_only;
   if (pair_enabled && gemm_pair16_eligible(M, N, K, residual, out16, out32))
     return gemm_pair16(A16, lda, W16, ldw, M, N, K, bias, out16, ldo16, act, dtype, stream);
   if (pair_enabled && gemm_pair_eligible(M, N, K)) {
@@ -306,5 +306,5 @@ extern "C" mmr_status mmr_gemm(const void* A16, int64_t lda, const void* W16, in
                                const float* bias, const float* residual, int64_t ldr, void* out16,
                                int64_t ldo16, float* out32, int64_t ldo32, int act, int dtype, void* stream) {
   return mmr::gemm(A16, lda, W16, ldw, M, N, K, bias, residual, ldr, out16, ldo16, out32, ldo32, act, dtype,
-                   static_cast<cudaStream_t>(stream));
+                   static_cast<cudaStream_t>(stream), false);
 }

@@ -6,7 +6,9 @@ namespace mmr {
 
 mmr_status gemm(const void* A16, int64_t lda, const void* W16, int64_t ldw, int M, int N, int K,
                 const float* bias, const float* residual, int64_t ldr, void* out16, int64_t ldo16,
-                float* out32, int64_t ldo32, int act, int dtype, cudaStream_t stream);
+                float* out32, int64_t ldo32, int act, int dtype, cudaStream_t stream, bool single_cta_only = false);
+// single_cta_only: always the 128-row single-CTA kernel, whatever M -- the [CLS]-row tail of the last block uses it so
+// that the kernel (hence the bits of every row) does not depend on the batch size
 mmr_status layernorm(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, int M, int H,
                      void* out16, int64_t ldo16, float* out32, int64_t ldo32, float scale, int accumulate,
                      int dtype, cudaStream_t stream);

