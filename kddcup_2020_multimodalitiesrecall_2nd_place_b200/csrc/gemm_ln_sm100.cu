@@ -181,15 +181,15 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int row_in_blk = int(rank) * kCtaRows + quarter * 32;
     const uint32_t sw128 = uint32_t(lane & 7), sw64 = uint32_t((lane >> 1) & 3);
     uint32_t rph = 0;                                       // parity bits of the residual barriers
-    int it = 0;
-    for (int m_blk = group; m_blk < m_tiles; m_blk += n_groups, ++it) {
+
+    // ---- pass 1 of this warp's `it`-th tile: y = acc + bias + residual -> back into TMEM; shifted sums (shift = this
+    // thread's first y); publish (mean_i, M2_i) of the thread's 128 columns
+    auto pass1 = [&](int it) {
+      const int m_blk = group + it * n_groups;
       const int acc = it & 1;
       const float* bias_w = vec_w + (m_blk >= p.split_blk ? 3 * kBN : 0);
-      const float* gamma_w = bias_w + kBN;
-      const float* beta_w = bias_w + 2 * kBN;
       const int row0 = m_blk * kPairRows + row_in_blk;
       const uint32_t taddr = tmem_base + uint32_t(acc) * kBN + (uint32_t(quarter * 32) << 16) + uint32_t(half * 128);
-
       MMR_LN_STAMP(0);
       // the first residual chunks -> slots (the previous block's stores must have finished reading them)
       if (lane == 0) {
@@ -203,8 +203,6 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_wait(&ring.tfull[acc], (it >> 1) & 1u);
       tc_fence_after();
       MMR_LN_STAMP(1);
-
-      // ---- pass 1: y = acc + bias + residual -> back into TMEM; shifted sums (shift = this thread's first y)
       float shift = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
@@ -237,20 +235,29 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       tmem_st_wait();
       MMR_LN_STAMP(2);
+      // Each half of an entry is ONE 8-byte store {value, tag}: a reader that sees this launch's tag sees the value
+      // (no fence, no atomic, no counter).
+      const float mean_i = shift + s1 * (1.0f / 128.0f);
+      const float m2_i = fmaxf(s2 - s1 * s1 * (1.0f / 128.0f), 0.f);
+      uint4* tab = p.stats + size_t(m_blk) * kLnSlots * kPairRows + row_in_blk + lane;
+      uint8_t* mine = reinterpret_cast<uint8_t*>(tab + size_t(n_tile * 2 + half) * kPairRows);
+      st_volatile_u32x2(mine, __float_as_uint(mean_i), tag);
+      st_volatile_u32x2(mine + 8, __float_as_uint(m2_i), tag);
+    };
 
-      // ---- exchange: publish (mean_i, M2_i) of this thread's 128 columns, wait for the 6 partials of its row
+    // ---- exchange + pass 2 of the `it`-th tile: wait for the 6 partials of this thread's row, Chan's formula,
+    // normalise from TMEM, affine, swizzled stages, TMA stores
+    auto pass2 = [&](int it) {
+      const int m_blk = group + it * n_groups;
+      const int acc = it & 1;
+      const float* bias_w = vec_w + (m_blk >= p.split_blk ? 3 * kBN : 0);
+      const float* gamma_w = bias_w + kBN;
+      const float* beta_w = bias_w + 2 * kBN;
+      const int row0 = m_blk * kPairRows + row_in_blk;
+      const uint32_t taddr = tmem_base + uint32_t(acc) * kBN + (uint32_t(quarter * 32) << 16) + uint32_t(half * 128);
       float mean, rstd;
       {
-        const float mean_i = shift + s1 * (1.0f / 128.0f);
-        const float m2_i = fmaxf(s2 - s1 * s1 * (1.0f / 128.0f), 0.f);
-        // Each half of an entry is ONE 8-byte store {value, tag}: a reader that sees this launch's tag sees the value
-        // (no fence, no atomic, no counter).  Every lane polls the 6 entries of its own row.
-        uint4* tab = p.stats + size_t(m_blk) * kLnSlots * kPairRows + row_in_blk + lane;
-        {
-          uint8_t* mine = reinterpret_cast<uint8_t*>(tab + size_t(n_tile * 2 + half) * kPairRows);
-          st_volatile_u32x2(mine, __float_as_uint(mean_i), tag);
-          st_volatile_u32x2(mine + 8, __float_as_uint(m2_i), tag);
-        }
+        const uint4* tab = p.stats + size_t(m_blk) * kLnSlots * kPairRows + row_in_blk + lane;
         // all 12 words are requested together on every probe: the wait costs one L2 round trip after the last
         // partner's publish, not one per entry
         float means[kLnSlots], m2_tot = 0.f;
@@ -284,9 +291,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         rstd = rsqrtf(m2_tot * (1.0f / kLnN) + p.eps);
       }
-
       MMR_LN_STAMP(3);
-      // ---- pass 2: normalise from TMEM, affine, swizzled stages, TMA stores
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint8_t* slot_s = wbuf + 4096 * (c % kSlots);
@@ -331,6 +336,16 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       }
       MMR_LN_STAMP(4);
+    };
+
+    // (Taking the tiles two at a time -- pass 1 of both, then pass 2 of both, so that a tile's statistics travel while
+    // the warp works on the other tile -- was built and measured in round 2: 45.8 vs 46.1 us at K = 768, nothing.  The
+    // "exchange wait" of the timeline absorbs the skew of warps that share one bound, L2 -> SM bandwidth: this launch
+    // moves ~290 MB through L2 at the ~9 TB/s every GEMM of the forward runs at.)
+    const int my_tiles = group < m_tiles ? (m_tiles - group + n_groups - 1) / n_groups : 0;
+    for (int it = 0; it < my_tiles; ++it) {
+      pass1(it);
+      pass2(it);
     }
     if (lane == 0) bulk_wait<0>();
   }

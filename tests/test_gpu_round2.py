@@ -265,7 +265,7 @@ def test_split3_and_fp32_attention_operators():
     torch.cuda.synchronize()
     ref = torch.nn.functional.gelu(x.double(), approximate="tanh")
     got = out[:, :256].double() + out[:, 256:512].double()
-    assert ((got - ref).abs() / ref.abs().clamp_min(1e-3)).max().item() < 2e-6
+    assert ((got - ref).abs() <= torch.maximum(ref.abs() * 2e-6, torch.full_like(ref, 1.3e-7))).all()
 
     H = 12
     for (B, Sq, Sk, masked) in [(3, 68, 68, True), (2, 32, 36, True), (2, 36, 32, False), (2, 104, 104, False), (5, 1, 68, True)]:
