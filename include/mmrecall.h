@@ -133,6 +133,10 @@ typedef struct {
 } mmr_decode_out;
 mmr_status mmr_decode_tsv(const char* const* lines, const size_t* line_len, int64_t n_lines, const mmr_decode_out* out,
                           int n_threads);
+/* CRC-32C (Castagnoli) of a HOST buffer, continuing from `crc` (0 to start): the per-block / per-tensor checksum of
+ * the TensorFlow checkpoints the two ImageBert drivers restore (imagebert_zk/evaluate_normal.py:204-212,
+ * imagebert_lds/src/run_pretraining_predict_score.py:347-362); used by the pure-Python bundle reader. */
+uint32_t mmr_crc32c(const void* data, size_t n, uint32_t crc);
 /* boxes5[i, r] = (x1/h, y1/w, x2/h, y2/w, (x2-x1)(y2-y1)/(w h)) exactly as load_data_v4.py:142-145 divides
  * (with_area != 0; zk) or the first four only (with_area == 0; lxmert utils.py:31).  Device pointers; fp32 division. */
 mmr_status mmr_boxes_normalize(const float* boxes4, const int32_t* image_h, const int32_t* image_w, int64_t n,

@@ -17,7 +17,7 @@ PRECISION_FAST, PRECISION_STRICT = 0, 1
 # every symbol include/mmrecall.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "mmr_last_error", "mmr_abi_version", "mmr_device_check", "mmr_set_tuning", "mmr_get_tuning", "mmr_tuning_generation",
-    "mmr_gemm", "mmr_gemm_layernorm", "mmr_gemm_layernorm_supported", "mmr_layernorm", "mmr_attention", "mmr_cast16", "mmr_cls_attention", "mmr_split3", "mmr_attention_f32", "mmr_am_softmax_head", "mmr_linear_head", "mmr_decode_tsv", "mmr_boxes_normalize", "mmr_ensemble_topk", "mmr_ndcg_at_k",
+    "mmr_gemm", "mmr_gemm_layernorm", "mmr_gemm_layernorm_supported", "mmr_layernorm", "mmr_attention", "mmr_cast16", "mmr_cls_attention", "mmr_split3", "mmr_attention_f32", "mmr_am_softmax_head", "mmr_linear_head", "mmr_decode_tsv", "mmr_crc32c", "mmr_boxes_normalize", "mmr_ensemble_topk", "mmr_ndcg_at_k",
     "mmr_create", "mmr_destroy", "mmr_forward", "mmr_set_debug_taps", "mmr_get_activation",
     "mmr_launches_per_forward", "mmr_set_profiling", "mmr_get_profile",
 ]
@@ -77,6 +77,8 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.mmr_get_tuning.argtypes = [i32]
     lib.mmr_get_tuning.restype = i32
     lib.mmr_tuning_generation.restype = C.c_uint
+    lib.mmr_crc32c.argtypes = [vp, C.c_size_t, C.c_uint32]
+    lib.mmr_crc32c.restype = C.c_uint32
     lib.mmr_am_softmax_head.argtypes = [vp, vp, vp, i32, vp, vp, vp]
     lib.mmr_linear_head.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, vp, vp]
     if True:

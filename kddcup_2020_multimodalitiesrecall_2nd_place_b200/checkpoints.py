@@ -5,13 +5,15 @@
   `variable_averages.variables_to_restore()` maps every variable `v` to the checkpoint entry
   `v/ExponentialMovingAverage` when it exists (evaluate_normal.py:204-206); the lds driver restores plain names
   through `get_assignment_map_from_checkpoint` and ignores `adam_m` / `adam_v` slots and `global_step`
-  (run_pretraining_predict_score.py:343-360).  Reading the TF bundle format itself needs TensorFlow (absent here and
-  on the GPU box): `tf_variables_from_npz` takes the `{name: array}` export any TF installation produces with
-  `np.savez(path, **{n: reader.get_tensor(n) for n in reader.get_variable_to_shape_map()})`.
+  (run_pretraining_predict_score.py:343-360).  `tf_variables_from_checkpoint` reads the checkpoint files themselves
+  (`<prefix>.index` + `.data-*`, or a directory with a `checkpoint` state file as tf.train.latest_checkpoint resolves
+  it, evaluate_normal.py:207-208) through the pure-Python bundle reader of tf_bundle.py -- no TensorFlow needed;
+  `tf_variables_from_npz` still takes a `{name: array}` export made elsewhere.
 * PyTorch `.pth` state_dicts (lxmert): `KDD.load` (kdd_model.py:131-152) = torch.load + non-strict
   load_state_dict, `module.` prefixes from nn.DataParallel stripped (entry.py:150-158).
 
-No real checkpoint ships with the reference, so these are exercised on synthetic dicts only.
+No real checkpoint ships with the reference, so these are exercised on synthetic weights: written as a V2 bundle by
+tf_bundle.write_bundle (EMA shadows, Adam slots and global_step included), read back, selected, scored.
 """
 from __future__ import annotations
 
@@ -58,6 +60,23 @@ def tf_variables_from_npz(path: str, prefer_ema: bool = True, wanted: Iterable[s
     with np.load(path) as z:
         entries = {k: z[k] for k in z.files}
     return select_tf_variables(entries, prefer_ema=prefer_ema, wanted=wanted)[0]
+
+
+def tf_variables_from_checkpoint(path: str, prefer_ema: bool = True, wanted: Iterable[str] = None,
+                                 verify_data: bool = False) -> Dict[str, np.ndarray]:
+    """A TF-1 checkpoint -> weights dict.  `path` is a checkpoint prefix (".../model.ckpt-251") or a directory holding
+    a `checkpoint` state file.  zk: prefer_ema=True (evaluate_normal.py:204-212); lds: prefer_ema=False
+    (run_pretraining_predict_score.py:347-362)."""
+    import os
+
+    from . import tf_bundle
+    prefix = path
+    if os.path.isdir(path):
+        prefix = tf_bundle.latest_checkpoint(path)
+        if prefix is None:
+            raise FileNotFoundError(f"{path}: no `checkpoint` state file (tf.train.latest_checkpoint would return None)")
+    reader = tf_bundle.BundleReader(prefix, verify_data=verify_data)
+    return select_tf_variables(reader.read_all(float_only=True), prefer_ema=prefer_ema, wanted=wanted)[0]
 
 
 def torch_state_dict_to_weights(state_dict: Mapping[str, object]) -> Dict[str, np.ndarray]:

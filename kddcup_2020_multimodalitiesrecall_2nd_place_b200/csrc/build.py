@@ -23,6 +23,7 @@ FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-msse4.2",
     "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
 ]

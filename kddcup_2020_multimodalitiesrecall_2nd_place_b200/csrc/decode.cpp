@@ -188,3 +188,51 @@ extern "C" mmr_status mmr_decode_tsv(const char* const* lines, const size_t* lin
   }
   return MMR_OK;
 }
+
+// CRC-32C (Castagnoli) of a host buffer, continuing from `crc` (0 to start): the checksum TensorFlow checkpoints carry
+// per index block and per tensor (tf_bundle.py verifies / writes them; evaluate_normal.py:204-212 restores such files).
+// Host utility, no GPU: hardware crc32 instruction where the compiler targets SSE4.2, slicing-by-8 tables otherwise.
+#if defined(__SSE4_2__)
+#include <nmmintrin.h>
+#endif
+extern "C" uint32_t mmr_crc32c(const void* data, size_t n, uint32_t crc) {
+  const uint8_t* p = static_cast<const uint8_t*>(data);
+  uint32_t c = ~crc;
+#if defined(__SSE4_2__)
+  uint64_t c64 = c;
+  while (n >= 8) {
+    uint64_t v;
+    std::memcpy(&v, p, 8);
+    c64 = _mm_crc32_u64(c64, v);
+    p += 8;
+    n -= 8;
+  }
+  c = static_cast<uint32_t>(c64);
+  while (n--) c = _mm_crc32_u8(c, *p++);
+#else
+  static uint32_t tab[8][256];
+  static bool init = false;
+  if (!init) {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t r = i;
+      for (int k = 0; k < 8; ++k) r = (r & 1u) ? (r >> 1) ^ 0x82F63B78u : r >> 1;
+      tab[0][i] = r;
+    }
+    for (uint32_t i = 0; i < 256; ++i)
+      for (int t = 1; t < 8; ++t) tab[t][i] = (tab[t - 1][i] >> 8) ^ tab[0][tab[t - 1][i] & 0xffu];
+    init = true;
+  }
+  while (n >= 8) {
+    uint32_t lo, hi;
+    std::memcpy(&lo, p, 4);
+    std::memcpy(&hi, p + 4, 4);
+    lo ^= c;
+    c = tab[7][lo & 0xffu] ^ tab[6][(lo >> 8) & 0xffu] ^ tab[5][(lo >> 16) & 0xffu] ^ tab[4][lo >> 24] ^
+        tab[3][hi & 0xffu] ^ tab[2][(hi >> 8) & 0xffu] ^ tab[1][(hi >> 16) & 0xffu] ^ tab[0][hi >> 24];
+    p += 8;
+    n -= 8;
+  }
+  while (n--) c = tab[0][(c ^ *p++) & 0xffu] ^ (c >> 8);
+#endif
+  return ~c;
+}
