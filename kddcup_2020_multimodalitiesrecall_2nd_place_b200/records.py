@@ -114,8 +114,10 @@ class FeedAssembler:
         self._q: Dict[str, List[int]] = {}
         top = max(label_map) + 1 if label_map else 1
         self.label_table = np.zeros((top, cfg.label_len), np.int32)      # class id -> padded token ids
+        self.known = np.zeros(top, bool)
         for cid, phrase in label_map.items():
             self.label_table[cid] = _pad(tokenizer.convert_tokens_to_ids(tokenizer.tokenize(phrase)), cfg.label_len)
+            self.known[cid] = True
 
     def query_ids(self, query: str) -> List[int]:
         ids = self._q.get(query)
@@ -137,7 +139,14 @@ class FeedAssembler:
         nb = np.minimum(batch["num_boxes"].numpy(), R).astype(np.int32)
         valid = np.arange(R)[None, :] < nb[:, None]
         cls = batch["class_labels"].numpy()
-        label_ids = self.label_table[np.clip(cls, 0, len(self.label_table) - 1)] * valid[..., None]
+        inside = (cls >= 0) & (cls < len(self.known))
+        unknown = valid & ~(inside & self.known[np.where(inside, cls, 0)])
+        if unknown.any():
+            # the reference looks the class id up in dict_multimodal_labels and dies with a KeyError
+            # (load_data_v4.py:149-150); scoring a box under another class's phrase instead would be silent garbage
+            i, r = np.argwhere(unknown)[0]
+            raise KeyError(f"record {int(i)}, box {int(r)}: detector class id {int(cls[i, r])} is not in the label map")
+        label_ids = self.label_table[np.where(valid & inside, cls, 0)] * valid[..., None]
         feeds = {"query_ids": torch.from_numpy(q), "label_ids": torch.from_numpy(label_ids.astype(np.int32)),
                  "feats": batch["feats"]}
         if cfg.kind == ZK:

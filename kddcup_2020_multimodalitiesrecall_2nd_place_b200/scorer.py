@@ -238,6 +238,14 @@ class MatchScorer:
             self._copy_stream = torch.cuda.Stream(self.device)
         return self._slots
 
+    @property
+    def copy_stream(self) -> "torch.cuda.Stream":
+        """The stream score_stream issues its input copies on.  A `fetch` callback that prepares part of a chunk ON THE
+        DEVICE (records.normalize_boxes) must do so on this stream, so that the copy into the slot is ordered after it
+        without stalling the copy pipeline behind the compute stream."""
+        self._make_slots()
+        return self._copy_stream
+
     def score(self, feeds_host: Dict[str, torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Scores N pairs held in (ideally pinned) host tensors: N is cut into max_batch chunks whose H2D copies run on
         a copy stream, double-buffered against the kernels of the previous chunk; probabilities come back to pinned
@@ -246,8 +254,10 @@ class MatchScorer:
         return self.score_stream(N, lambda lo, hi: {n: feeds_host[n][lo:hi] for n in self.spec}, out)
 
     def score_stream(self, n_pairs: int, fetch, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """The same pipeline over a pair list that need not be resident as one array: `fetch(lo, hi)` returns the host
-        feeds of pairs [lo, hi) (hi - lo <= max_batch; a decoder's batch arrays, a window of a memory-mapped file, ...)."""
+        """The same pipeline over a pair list that need not be resident as one array: `fetch(lo, hi)` returns the feeds
+        of pairs [lo, hi) (hi - lo <= max_batch; a decoder's batch arrays, a window of a memory-mapped file, ...; host or
+        device tensors).  `fetch` may reuse its buffers every SECOND call: before call k, the copies that read what call
+        k - 2 returned have completed."""
         N = int(n_pairs)
         if out is None:
             out = torch.empty((N, 2), dtype=torch.float32).pin_memory()
@@ -262,6 +272,8 @@ class MatchScorer:
         for i, lo in enumerate(range(0, N, Bm)):
             hi = min(N, lo + Bm)
             s = slots[i % 2]
+            if i >= 2:
+                s["ready"].synchronize()                  # H2D of chunk i-2 done: its source buffers may be rewritten
             chunk = fetch(lo, hi)
             with torch.cuda.stream(copy):
                 if i >= 2:
