@@ -63,6 +63,11 @@ typedef enum {
 
 const char* mmr_last_error(void);
 int mmr_abi_version(void);
+/* 1 when the library was built with MMR_EXPERIMENTAL (csrc/build.py): the kernel variants that lost their A/B
+ * measurements -- mma.sync attention, first tcgen05 attention, row-owner GEMM+LayerNorm, 4-CTA multicast GEMM -- are
+ * compiled in and their knobs below are live.  In the default build (0) those knobs are accepted and ignored:
+ * MMR_TUNE_ATTN_TMA, MMR_TUNE_ATTN_TC, MMR_TUNE_LN_ROW_CFG, MMR_TUNE_GEMM_CLUSTER = 2, MMR_TUNE_GEMM_LN = 2 / 3. */
+int mmr_experimental_build(void);
 /* Kernel-selection knobs, for A/B measurements and tests (defaults are the fastest measured; the environment
  * variable of the same meaning is read once at first use): value 0 disables / selects the older path.
  *   MMR_TUNE_GEMM_PAIR     (env MMR_GEMM_PAIR,    default 1) CTA-pair (cta_group::2) GEMM kernels

@@ -16,7 +16,7 @@ PRECISION_FAST, PRECISION_STRICT = 0, 1
 
 # every symbol include/mmrecall.h declares (tests check the .so exports all of them)
 EXPORTS = [
-    "mmr_last_error", "mmr_abi_version", "mmr_device_check", "mmr_set_tuning", "mmr_get_tuning", "mmr_tuning_generation",
+    "mmr_last_error", "mmr_abi_version", "mmr_experimental_build", "mmr_device_check", "mmr_set_tuning", "mmr_get_tuning", "mmr_tuning_generation",
     "mmr_gemm", "mmr_gemm_layernorm", "mmr_gemm_layernorm_supported", "mmr_layernorm", "mmr_attention", "mmr_cast16", "mmr_cls_attention", "mmr_split3", "mmr_attention_f32", "mmr_am_softmax_head", "mmr_linear_head", "mmr_decode_tsv", "mmr_crc32c", "mmr_boxes_normalize", "mmr_ensemble_topk", "mmr_ndcg_at_k",
     "mmr_create", "mmr_destroy", "mmr_forward", "mmr_set_debug_taps", "mmr_get_activation",
     "mmr_launches_per_forward", "mmr_set_profiling", "mmr_get_profile",
@@ -62,6 +62,7 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib = C.CDLL(str(LIB_PATH))
     lib.mmr_last_error.restype = C.c_char_p
     lib.mmr_abi_version.restype = C.c_int
+    lib.mmr_experimental_build.restype = C.c_int
     lib.mmr_device_check.argtypes = [C.c_int]
     vp, i64, i32, f32 = C.c_void_p, C.c_int64, C.c_int, C.c_float
     lib.mmr_gemm.argtypes = [vp, i64, vp, i64, i32, i32, i32, vp, vp, i64, vp, i64, vp, i64, i32, i32, vp]

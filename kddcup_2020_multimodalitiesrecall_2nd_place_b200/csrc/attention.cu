@@ -19,6 +19,11 @@ constexpr int kHeadDim = 64;
 constexpr int kPitch = 72;       // smem row pitch in elements (144 B): conflict-free ldmatrix
 constexpr int kMaxSeq = 128;
 
+// The mma.sync kernels below (one CTA per (pair, head), and its persistent TMA-pipelined sibling) lost to the tcgen05
+// kernel of attention_tc2.cu (31.7 / 40 us against 24-25 us at B = 256, S = 68) and are lab notes: they are compiled
+// only into MMR_EXPERIMENTAL builds (csrc/build.py, environment MMR_EXPERIMENTAL=1).
+#ifdef MMR_EXPERIMENTAL
+
 __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
@@ -456,6 +461,8 @@ static mmr_status launch_attention(const void* q, int64_t ldq, const void* k, in
   return MMR_OK;
 }
 
+#endif  // MMR_EXPERIMENTAL
+
 mmr_status attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                      const int32_t* key_mask, void* out16, int64_t ldo, int B, int Sq, int Sk, int heads,
                      int dtype, cudaStream_t stream) {
@@ -470,6 +477,13 @@ mmr_status attention(const void* q, int64_t ldq, const void* k, int64_t ldk, con
                   (reinterpret_cast<uintptr_t>(out16) & 3) == 0,
               "mmr_attention: q/k/v must be 16-byte aligned");
   MMR_REQUIRE(dtype == MMR_DT_BF16 || dtype == MMR_DT_FP16, "mmr_attention: bad dtype %d", dtype);
+#ifndef MMR_EXPERIMENTAL
+  MMR_REQUIRE(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out16) & 15) == 0,
+              "mmr_attention: output rows must be 16-byte aligned (the kernels that take any alignment are built only "
+              "with MMR_EXPERIMENTAL)");
+  return attention_tc2(q, ldq, k, ldk, v, ldv, key_mask, out16, ldo, B, Sq, Sk, heads, dtype, stream);
+}
+#else
   if (attention_tc2_eligible(out16, ldo))
     return attention_tc2(q, ldq, k, ldk, v, ldv, key_mask, out16, ldo, B, Sq, Sk, heads, dtype, stream);
   if (attention_tc_eligible(out16, ldo))
@@ -493,6 +507,7 @@ mmr_status attention(const void* q, int64_t ldq, const void* k, int64_t ldk, con
   MMR_ATT(FP16, 16);
 #undef MMR_ATT
 }
+#endif
 
 }  // namespace mmr
 

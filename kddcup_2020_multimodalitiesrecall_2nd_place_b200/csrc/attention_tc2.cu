@@ -546,7 +546,10 @@ static mmr_status launch_attention_tc2_e(const void* q, int64_t ldq, const void*
 
 // Arguments are validated by mmr::attention (attention.cu); on top of those this path needs 16-byte aligned output rows.
 bool attention_tc2_eligible(const void* out16, int64_t ldo) {
-  return tuning(MMR_TUNE_ATTN_TC) == 2 && ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out16) & 15) == 0;
+#ifdef MMR_EXPERIMENTAL
+  if (tuning(MMR_TUNE_ATTN_TC) != 2) return false;   // the older kernels exist only in experimental builds
+#endif
+  return ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out16) & 15) == 0;
 }
 mmr_status attention_tc2(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                          const int32_t* key_mask, void* out16, int64_t ldo, int B, int Sq, int Sk, int heads, int dtype,

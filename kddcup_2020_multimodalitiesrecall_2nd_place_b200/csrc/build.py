@@ -17,7 +17,12 @@ HERE = Path(__file__).resolve().parent
 PKG = HERE.parent
 LIB = PKG / "libmmrecall.so"
 OBJ_DIR = HERE / "build"
-SOURCES = ["common.cu", "gemm_sm100.cu", "gemm2_sm100.cu", "gemm16_sm100.cu", "gemm_ln_sm100.cu", "gemm_lnrow_sm100.cu", "rowops.cu", "attention.cu", "attention_tc.cu", "attention_tc2.cu", "embed.cu", "cls_tail.cu", "strict.cu", "ensemble.cu", "model.cu", "decode.cpp"]
+SOURCES = ["common.cu", "gemm_sm100.cu", "gemm2_sm100.cu", "gemm16_sm100.cu", "gemm_ln_sm100.cu", "rowops.cu", "attention.cu", "attention_tc2.cu", "embed.cu", "cls_tail.cu", "strict.cu", "ensemble.cu", "model.cu", "decode.cpp"]
+# Kernel variants that were built, measured and lost: the mma.sync attention kernels, the first
+# tcgen05 attention, the row-owner GEMM+LayerNorm and the 4-CTA multicast GEMM.  MMR_EXPERIMENTAL=1 compiles them in
+# (and makes their mmr_set_tuning knobs live) for A/B measurements; the default build and test matrix cover what ships.
+EXPERIMENTAL = os.environ.get("MMR_EXPERIMENTAL", "0") not in ("", "0")
+EXPERIMENTAL_SOURCES = ["gemm_lnrow_sm100.cu", "attention_tc.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -39,17 +44,19 @@ def _digest(paths) -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
-    srcs = [HERE / s for s in SOURCES if (HERE / s).exists()]
+    names = SOURCES + (EXPERIMENTAL_SOURCES if EXPERIMENTAL else [])
+    flags = FLAGS + (["-DMMR_EXPERIMENTAL"] if EXPERIMENTAL else [])
+    srcs = [HERE / s for s in names if (HERE / s).exists()]
     deps = srcs + sorted(HERE.glob("*.cuh")) + [PKG.parent / "include" / "mmrecall.h"]
     stamp = OBJ_DIR / "stamp.txt"
-    dig = _digest(deps)
+    dig = _digest(deps) + ("+experimental" if EXPERIMENTAL else "")
     if not force and LIB.exists() and stamp.exists() and stamp.read_text() == dig:
         return LIB
     OBJ_DIR.mkdir(exist_ok=True)
 
     def compile_one(src: Path):
         obj = OBJ_DIR / (src.stem + ".o")
-        cmd = [NVCC, *FLAGS, "-c", str(src), "-o", str(obj)]
+        cmd = [NVCC, *flags, "-c", str(src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         (OBJ_DIR / (src.stem + ".ptxas.log")).write_text(r.stderr)
         if r.returncode != 0:

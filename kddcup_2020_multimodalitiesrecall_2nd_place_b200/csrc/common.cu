@@ -65,6 +65,13 @@ mmr_status require_sm100() {
 
 extern "C" const char* mmr_last_error(void) { return mmr::last_error_buf(); }
 extern "C" int mmr_abi_version(void) { return 2; }
+extern "C" int mmr_experimental_build(void) {
+#ifdef MMR_EXPERIMENTAL
+  return 1;
+#else
+  return 0;
+#endif
+}
 extern "C" mmr_status mmr_set_tuning(int knob, int value) {
   if (knob < 0 || knob >= MMR_TUNE_COUNT) return mmr::fail(MMR_ERR_INVALID, "mmr_set_tuning: unknown knob %d", knob);
   if (!mmr::g_tuning_init) mmr::tuning_init();

@@ -257,13 +257,19 @@ template <int ACT, class E16>
 static mmr_status launch_p16(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& twt, const CUtensorMap& tw2,
                              const CUtensorMap& twt2, const CUtensorMap& to, const P16Params& p, int grid,
                              int cluster_pairs, cudaStream_t stream) {
+#ifdef MMR_EXPERIMENTAL
   if (cluster_pairs == 2) return launch_p16s<ACT, E16, kP16Stages, 2>(ta, tw, twt, tw2, twt2, to, p, grid, stream);
+#endif
+  (void)cluster_pairs;
   return launch_p16s<ACT, E16, kP16Stages, 1>(ta, tw, twt, tw2, twt2, to, p, grid, stream);
 }
 
 // Co-resident 4-CTA clusters of this kernel on the current device (0: none).  All instantiations share the launch
 // shape, so one query serves them all.
 static int p16_max_quads() {
+#ifndef MMR_EXPERIMENTAL
+  return 0;   // the 4-CTA multicast variant (measured slower: 33 clusters = 132 of 148 SMs) is a lab note
+#else
   static int cached = -1;
   if (cached >= 0) return cached;
   auto kern = gemm_pair16_kernel<MMR_ACT_NONE, FP16, kP16Stages, 2>;
@@ -289,6 +295,7 @@ static int p16_max_quads() {
     n = 0;
   }
   return cached = n;
+#endif
 }
 
 template <class E16>

@@ -469,10 +469,12 @@ mmr_status gemm_ln_2w(const void* A16, int64_t lda, const void* W16, const void*
                 reinterpret_cast<uintptr_t>(beta) | reinterpret_cast<uintptr_t>(biasb) | reinterpret_cast<uintptr_t>(gammab) |
                 reinterpret_cast<uintptr_t>(betab)) & 15) == 0,
               "gemm_ln: pointers must be 16-byte aligned");
+#ifdef MMR_EXPERIMENTAL
   // row-owner decomposition (gemm_lnrow_sm100.cu): 2 = always, 3 = only for K <= 1024 (one weight matrix only)
   if (!two && (tuning(MMR_TUNE_GEMM_LN) == 2 || (tuning(MMR_TUNE_GEMM_LN) == 3 && K <= 1024)))
     return gemm_lnrow(A16, lda, W16, ldw, M, K, bias, residual, ldr, gamma, beta, eps, out16, ldo16, out32, ldo32, dtype,
                       stream);
+#endif
   MMR_REQUIRE(table.stats != nullptr && table.epoch != nullptr && (M + kPairRows - 1) / kPairRows <= table.m_tiles,
               "gemm_ln: exchange table missing or too small for M=%d", M);
   const int ek = dtype == MMR_DT_BF16 ? 1 : 0;

@@ -8,6 +8,14 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 
+def _need_experimental(what):
+    """The kernel variants that lost their A/B measurements are compiled only into MMR_EXPERIMENTAL builds
+    (csrc/build.py); the default build and test matrix cover what ships."""
+    from kddcup_2020_multimodalitiesrecall_2nd_place_b200 import _lib
+    if not _lib.load().mmr_experimental_build():
+        pytest.skip(f"{what}: only in MMR_EXPERIMENTAL builds")
+
+
 def _rel(got, ref):
     return ((got.float() - ref.float()).abs().max() / (ref.float().abs().max() + 1e-30)).item()
 
@@ -125,6 +133,8 @@ def test_attention(dtype, kernel):
     version (one item per CTA, P through shared memory), one CTA per (pair, head) with mma.sync, and the persistent
     TMA-pipelined mma.sync variant."""
     from kddcup_2020_multimodalitiesrecall_2nd_place_b200 import ops, _lib
+    if kernel != "tcgen05_pipelined":
+        _need_experimental(f"attention kernel '{kernel}'")
     lib = _lib.load()
     default_tc = lib.mmr_get_tuning(_lib.TUNE_ATTN_TC)
     _lib.check(lib.mmr_set_tuning(_lib.TUNE_ATTN_TC, {"tcgen05_pipelined": 2, "tcgen05": 1}.get(kernel, 0)))
@@ -191,6 +201,8 @@ def test_fused_gemm_layernorm(M, K, variant):
     stream, ragged M included.  Variant (1, 0): three CTA pairs per 256-row block meeting through a global table
     (default); (2, cfg): one pair owns the block and all 768 columns, for every shared-memory split it is built in."""
     from kddcup_2020_multimodalitiesrecall_2nd_place_b200 import ops, _lib
+    if variant[0] != 1:
+        _need_experimental("row-owner GEMM+LayerNorm")
     lib = _lib.load()
     if not lib.mmr_gemm_layernorm_supported(M, K, _lib.DT_FP16):
         pytest.skip("device cannot co-schedule a 6-CTA cluster with this kernel's shared memory")
@@ -229,6 +241,8 @@ def test_alternate_kernel_paths_agree(knob, value):
     TMA-multicast W (odd and even row-block counts), unsplit tail, the general pair kernel, the single-CTA kernel,
     and GEMM + separate LayerNorm."""
     from kddcup_2020_multimodalitiesrecall_2nd_place_b200 import ops, _lib
+    if knob == "TUNE_GEMM_CLUSTER":
+        _need_experimental("4-CTA multicast GEMM")
     lib = _lib.load()
     k = getattr(_lib, knob)
     default = {"TUNE_GEMM_CLUSTER": 1}.get(knob, 1)
