@@ -134,19 +134,50 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// One attention problem of a launch: B pairs x heads items of Sq query rows x Sk keys (device pointers).
+struct T2Seg {
+  const int32_t* key_mask;   // [B, Sk] or null
+  void* out;                 // [B * Sq, ldo] 16-bit
+  int64_t ldo;
+  int Sq, Sk;
+};
+struct T2Segs {
+  T2Seg s[2];
+  int n_items0;              // items [0, n_items0) are segment 0, [n_items0, n_items) segment 1
+};
+
 // NCH = number of 16-key chunks of an S row, kept in registers (2, 3 or 5: the key counts of the three scorers at
 // the bench and native shapes); 0 = any row of up to 128 keys, two passes over TMEM.
-template <class E16, int NCH, int WPG>
+// TWO = the launch carries two segments (see below); single-problem launches compile the segment selects away.
+template <class E16, int NCH, int WPG, bool TWO>
 __global__ void __launch_bounds__(T2Roles<WPG>::kThreads, 1)
 attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                     const __grid_constant__ CUtensorMap tmap_v, const int32_t* __restrict__ key_mask,
-                     typename E16::T* __restrict__ out, int64_t ldo, int Sq, int Sk, int heads, int n_items,
-                     uint32_t idesc_fmt, unsigned long long* trace, int ablate) {
+                     const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_q1,
+                     const __grid_constant__ CUtensorMap tmap_k1, const __grid_constant__ CUtensorMap tmap_v1,
+                     const T2Segs segs, int heads, int n_items, uint32_t idesc_fmt, unsigned long long* trace,
+                     int ablate) {
   using T = typename E16::T;
   extern __shared__ __align__(1024) uint8_t smem_t2[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_t2) + 1023) & ~uintptr_t(1023));
+  // Two SEGMENTS may share one launch (LXMERT: the self-attention of the language and of the visual stream, or the two
+  // directions of a cross-attention block): items [0, n_items0) belong to segment 0, the rest to segment 1, each with
+  // its own tensor maps, lengths, mask and output.  Stages, TMEM slots and the S-row width are laid out for the LARGER
+  // shapes; an item with fewer keys leaves the key rows [Sk_i, SkP) of its stage as the previous item left them --
+  // finite numbers behind a -inf mask, i.e. probabilities that are exactly 0.
+  const int Sq = max(segs.s[0].Sq, segs.s[1].Sq), Sk = max(segs.s[0].Sk, segs.s[1].Sk);
+  const int SkMin = min(segs.s[0].Sk, segs.s[1].Sk);
   const T2Layout L = t2_layout(Sq, Sk, T2Roles<WPG>::kOutStageBytes);
   const int SkP = (Sk + 15) & ~15;
+  const int n_items0 = segs.n_items0;
+  // work item n of this CTA -> (segment, pair, head)
+  auto item_of = [&](int n, int& b, int& h) -> int {
+    const int item = int(blockIdx.x) + n * int(gridDim.x);
+    const int seg = (TWO && item >= n_items0) ? 1 : 0;
+    const int li = item - (seg ? n_items0 : 0);
+    b = li / heads;
+    h = li - b * heads;
+    return seg;
+  };
   const int n_stages = L.n_stages;
   float* mask_s = reinterpret_cast<float*>(ring + size_t(n_stages) * L.stage_bytes + L.pad_bytes);   // [stages][128]
   int32_t* raw_s = reinterpret_cast<int32_t*>(mask_s + kT2MaxStages * 128);                          // [4][128]
@@ -166,11 +197,11 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   // zero the padding key rows [Sk, SkP) of K and V in every stage once: TMA never writes them, and they must read as
   // finite numbers (their probabilities are exactly 0; 0 x NaN is not).  Q rows >= Sq may hold anything.
   {
-    const uint32_t pad16 = uint32_t(SkP - Sk) * 8u;   // 16-byte units per K (or V) tile
+    const uint32_t pad16 = uint32_t(SkP - SkMin) * 8u;   // 16-byte units per K (or V) tile
     for (uint32_t i = threadIdx.x; i < uint32_t(n_stages) * 2u * pad16; i += blockDim.x) {
       const uint32_t st = i / (2u * pad16), r = i - st * 2u * pad16;
       const uint32_t tile = r / pad16, o = r - tile * pad16;
-      uint8_t* base = ring + size_t(st) * L.stage_bytes + L.q_bytes + tile * L.kv_bytes + uint32_t(Sk) * 128u;
+      uint8_t* base = ring + size_t(st) * L.stage_bytes + L.q_bytes + tile * L.kv_bytes + uint32_t(SkMin) * 128u;
       reinterpret_cast<uint4*>(base)[o] = make_uint4(0, 0, 0, 0);
     }
   }
@@ -178,6 +209,11 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
+    if (TWO) {
+      tma_prefetch_desc(&tmap_q1);
+      tma_prefetch_desc(&tmap_k1);
+      tma_prefetch_desc(&tmap_v1);
+    }
     for (int s = 0; s < kT2MaxStages; ++s) {
       mbar_init(&full_bar[s], 2);    // the producer's expect_tx arrive + the mask warp's
       mbar_init(&empty_bar[s], 1);
@@ -210,18 +246,22 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       int stage = 0;
       uint32_t phase = 0;
       for (int n = 0; n < my_items; ++n) {
-        const int item = int(blockIdx.x) + n * int(gridDim.x);
-        const int b = item / heads, h = item - b * heads;
+        int b, h;
+        const int seg = item_of(n, b, h);
+        const int sq = seg ? segs.s[1].Sq : segs.s[0].Sq, sk = seg ? segs.s[1].Sk : segs.s[0].Sk;
+        const CUtensorMap* mq = seg ? &tmap_q1 : &tmap_q;
+        const CUtensorMap* mk = seg ? &tmap_k1 : &tmap_k;
+        const CUtensorMap* mv = seg ? &tmap_v1 : &tmap_v;
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         uint8_t* st = ring + size_t(stage) * L.stage_bytes;
         if (ablate & 8) {
-          mbar_arrive_expect_tx(&full_bar[stage], uint32_t(Sq) * 128u);
-          tma_load_2d(st, &tmap_q, &full_bar[stage], h * kT2HeadDim, b * Sq);
+          mbar_arrive_expect_tx(&full_bar[stage], uint32_t(sq) * 128u);
+          tma_load_2d(st, mq, &full_bar[stage], h * kT2HeadDim, b * sq);
         } else {
-        mbar_arrive_expect_tx(&full_bar[stage], uint32_t(Sq + 2 * Sk) * 128u);
-        tma_load_2d(st, &tmap_q, &full_bar[stage], h * kT2HeadDim, b * Sq);
-        tma_load_2d(st + L.q_bytes, &tmap_k, &full_bar[stage], h * kT2HeadDim, b * Sk);
-        tma_load_2d(st + L.q_bytes + L.kv_bytes, &tmap_v, &full_bar[stage], h * kT2HeadDim, b * Sk);
+        mbar_arrive_expect_tx(&full_bar[stage], uint32_t(sq + 2 * sk) * 128u);
+        tma_load_2d(st, mq, &full_bar[stage], h * kT2HeadDim, b * sq);
+        tma_load_2d(st + L.q_bytes, mk, &full_bar[stage], h * kT2HeadDim, b * sk);
+        tma_load_2d(st + L.q_bytes + L.kv_bytes, mv, &full_bar[stage], h * kT2HeadDim, b * sk);
         }
         MMR_T2_STAMP(n, 0);
         if (++stage == n_stages) {
@@ -236,10 +276,14 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     // A key_mask load is an L2 round trip (~1 us): the raw int32 rows travel global -> shared with cp.async THREE
     // ITEMS AHEAD into a 4-entry staging ring (each lane reads back only what it fetched itself).
     auto issue_mask = [&](int n) {
-      if (n < my_items && key_mask != nullptr && !(ablate & 2)) {
-        const int b = (int(blockIdx.x) + n * int(gridDim.x)) / heads;
+      if (n < my_items && !(ablate & 2)) {
+        int b, h;
+        const int seg = item_of(n, b, h);
+        const int32_t* km = seg ? segs.s[1].key_mask : segs.s[0].key_mask;   // (selects, not indexing: a dynamically
+        const int sk = seg ? segs.s[1].Sk : segs.s[0].Sk;                    //  indexed parameter struct moves to local memory)
         int32_t* dst = raw_s + (n & 3) * 128;
-        for (int i = lane; i < Sk; i += 32) cp_async_4(dst + i, key_mask + int64_t(b) * Sk + i);
+        if (km != nullptr)
+          for (int i = lane; i < sk; i += 32) cp_async_4(dst + i, km + int64_t(b) * sk + i);
       }
       asm volatile("cp.async.commit_group;" ::: "memory");   // (possibly empty) group: one per item, in order
     };
@@ -254,9 +298,13 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       mbar_wait(&empty_bar[stage], phase ^ 1u);
       float* sMask = mask_s + stage * 128;
       const int32_t* raw = raw_s + (n & 3) * 128;
+      int b_, h_;
+      const int seg = item_of(n, b_, h_);
+      const bool has_mask = (seg ? segs.s[1].key_mask : segs.s[0].key_mask) != nullptr;
+      const int sk = seg ? segs.s[1].Sk : segs.s[0].Sk;
       for (int i = lane; i < SkP; i += 32) {
-        float m = -INFINITY;   // padding keys (>= Sk) do not exist for the softmax
-        if (i < Sk) m = (key_mask == nullptr || raw[i] != 0) ? 0.0f : -10000.0f * kLog2e;
+        float m = -INFINITY;   // padding keys (>= this item's Sk) do not exist for the softmax
+        if (i < sk) m = (!has_mask || raw[i] != 0) ? 0.0f : -10000.0f * kLog2e;
         sMask[i] = m;
       }
       __syncwarp();
@@ -324,7 +372,6 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     // ===================== softmax / output warpgroups: one thread = one query row =====================
     const int g = warp >> 2, w = warp & 3;
     const int row = w * 32 + lane;                         // TMEM lane of this thread = query row
-    const bool live = w * 32 < Sq;                         // this warp owns at least one real query row
     const uint32_t tmem_s = tmem_base + uint32_t(g * kT2SlotCols) + (uint32_t(w * 32) << 16);
     const uint32_t tmem_o = tmem_s + 64u;
     const int n_chunks = SkP >> 4;
@@ -332,8 +379,12 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       const uint32_t use = uint32_t(n >> 2);
       const int stage = n % n_stages;
       const uint32_t ring_phase = uint32_t(n / n_stages) & 1u;
-      const int item = int(blockIdx.x) + n * int(gridDim.x);
-      const int b = item / heads, h = item - b * heads;
+      int b, h;
+      const int seg = item_of(n, b, h);
+      const int sq_i = seg ? segs.s[1].Sq : segs.s[0].Sq;
+      T* __restrict__ out = static_cast<T*>(seg ? segs.s[1].out : segs.s[0].out);
+      const int64_t ldo = seg ? segs.s[1].ldo : segs.s[0].ldo;
+      const bool live = w * 32 < sq_i;                     // this warp owns at least one real query row of the item
       const float* sMask = mask_s + stage * 128;
       mbar_wait(&full_bar[stage], ring_phase);             // the mask row (generic writes of the producer warp)
       mbar_wait(&s_ready[g], use & 1u);
@@ -466,11 +517,11 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             const int rl = i * 4 + (lane >> 3), u = lane & 7;
             const uint4 val = *reinterpret_cast<const uint4*>(stg + rl * 128 + ((uint32_t(u) ^ uint32_t(rl & 7)) << 4));
             const int r = w * 32 + rl;
-            if (r < Sq && !(ablate & 1)) *reinterpret_cast<uint4*>(out + (int64_t(b) * Sq + r) * ldo + h * kT2HeadDim + u * 8) = val;
+            if (r < sq_i && !(ablate & 1)) *reinterpret_cast<uint4*>(out + (int64_t(b) * sq_i + r) * ldo + h * kT2HeadDim + u * 8) = val;
           }
           __syncwarp();   // the stage is rewritten by this warp's next item
-        } else if (row < Sq) {
-          uint4* orow = reinterpret_cast<uint4*>(out + (int64_t(b) * Sq + row) * ldo + h * kT2HeadDim);
+        } else if (row < sq_i) {
+          uint4* orow = reinterpret_cast<uint4*>(out + (int64_t(b) * sq_i + row) * ldo + h * kT2HeadDim);
 #pragma unroll
           for (int u = 0; u < 4; ++u)
             orow[u] = make_uint4(E16::pack(__uint_as_float(o0[8 * u]) * inv, __uint_as_float(o0[8 * u + 1]) * inv),
@@ -504,44 +555,64 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 static unsigned long long* g_t2_trace = nullptr;
 static int g_t2_ablate = 0;   // timing experiments only (tools/attn_ablate.py): results are wrong when non-zero
 
-template <class E16, int NCH, int WPG>
-static mmr_status launch_attention_tc2(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
-                                       int64_t ldv, const int32_t* key_mask, void* out, int64_t ldo, int B, int Sq,
-                                       int Sk, int heads, int dtype, cudaStream_t stream) {
-  using T = typename E16::T;
-  auto kern = attention_tc2_kernel<E16, NCH, WPG>;
+// One attention problem as the host sees it.
+struct T2Problem {
+  const void *q, *k, *v;
+  int64_t ldq, ldk, ldv;
+  const int32_t* key_mask;
+  void* out;
+  int64_t ldo;
+  int B, Sq, Sk;
+};
+
+template <class E16, int NCH, int WPG, bool TWO>
+static mmr_status launch_attention_tc2(const T2Problem& p0, const T2Problem* p1, int heads, int dtype, cudaStream_t stream) {
+  auto kern = attention_tc2_kernel<E16, NCH, WPG, TWO>;
   static bool configured = false;
   if (!configured) {
     MMR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
   const int ek = dtype == MMR_DT_BF16 ? 1 : 0;
-  CUtensorMap tq, tk, tv;
-  MMR_TRY(make_tmap_ex(&tq, q, int64_t(B) * Sq, int64_t(heads) * kT2HeadDim, ldq, ek, kT2HeadDim, Sq, 128));
-  MMR_TRY(make_tmap_ex(&tk, k, int64_t(B) * Sk, int64_t(heads) * kT2HeadDim, ldk, ek, kT2HeadDim, Sk, 128));
-  MMR_TRY(make_tmap_ex(&tv, v, int64_t(B) * Sk, int64_t(heads) * kT2HeadDim, ldv, ek, kT2HeadDim, Sk, 128));
-  const T2Layout L = t2_layout(Sq, Sk, T2Roles<WPG>::kOutStageBytes);
-  MMR_REQUIRE(L.n_stages >= 2, "attention_tc2: operand ring does not fit (Sq=%d Sk=%d)", Sq, Sk);
-  const int n_items = B * heads;
+  const T2Problem& pb = p1 != nullptr ? *p1 : p0;
+  CUtensorMap tq, tk, tv, tq1, tk1, tv1;
+  const int64_t cols = int64_t(heads) * kT2HeadDim;
+  MMR_TRY(make_tmap_ex(&tq, p0.q, int64_t(p0.B) * p0.Sq, cols, p0.ldq, ek, kT2HeadDim, p0.Sq, 128));
+  MMR_TRY(make_tmap_ex(&tk, p0.k, int64_t(p0.B) * p0.Sk, cols, p0.ldk, ek, kT2HeadDim, p0.Sk, 128));
+  MMR_TRY(make_tmap_ex(&tv, p0.v, int64_t(p0.B) * p0.Sk, cols, p0.ldv, ek, kT2HeadDim, p0.Sk, 128));
+  MMR_TRY(make_tmap_ex(&tq1, pb.q, int64_t(pb.B) * pb.Sq, cols, pb.ldq, ek, kT2HeadDim, pb.Sq, 128));
+  MMR_TRY(make_tmap_ex(&tk1, pb.k, int64_t(pb.B) * pb.Sk, cols, pb.ldk, ek, kT2HeadDim, pb.Sk, 128));
+  MMR_TRY(make_tmap_ex(&tv1, pb.v, int64_t(pb.B) * pb.Sk, cols, pb.ldv, ek, kT2HeadDim, pb.Sk, 128));
+  const T2Layout L = t2_layout(std::max(p0.Sq, pb.Sq), std::max(p0.Sk, pb.Sk), T2Roles<WPG>::kOutStageBytes);
+  MMR_REQUIRE(L.n_stages >= 2, "attention_tc2: operand ring does not fit (Sq=%d Sk=%d)", std::max(p0.Sq, pb.Sq),
+              std::max(p0.Sk, pb.Sk));
+  T2Segs segs;
+  segs.s[0] = T2Seg{p0.key_mask, p0.out, p0.ldo, p0.Sq, p0.Sk};
+  segs.s[1] = T2Seg{pb.key_mask, pb.out, pb.ldo, pb.Sq, pb.Sk};
+  segs.n_items0 = p0.B * heads;
+  const int n_items = segs.n_items0 + (p1 != nullptr ? p1->B * heads : 0);
   const int grid = std::min(n_items, sm_count());   // one CTA per SM: it allocates all 512 TMEM columns
-  MMR_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(T2Roles<WPG>::kThreads), L.smem_bytes, stream, tq, tk, tv, key_mask,
-                         static_cast<T*>(out), ldo, Sq, Sk, heads, n_items, uint32_t(dtype), g_t2_trace, g_t2_ablate));
+  MMR_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(T2Roles<WPG>::kThreads), L.smem_bytes, stream, tq, tk, tv, tq1, tk1, tv1,
+                         segs, heads, n_items, uint32_t(dtype), g_t2_trace, g_t2_ablate));
   return MMR_OK;
 }
 template <class E16>
-static mmr_status launch_attention_tc2_e(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
-                                         int64_t ldv, const int32_t* key_mask, void* out, int64_t ldo, int B, int Sq,
-                                         int Sk, int heads, int dtype, cudaStream_t stream) {
+static mmr_status launch_attention_tc2_e(const T2Problem& p0, const T2Problem* p1, int heads, int dtype,
+                                         cudaStream_t stream) {
+  const int Sq = std::max(p0.Sq, p1 ? p1->Sq : 0), Sk = std::max(p0.Sk, p1 ? p1->Sk : 0);
   const int chunks = (Sk + 15) / 16;
-  if (Sq <= 96 && chunks == 2)
-    return launch_attention_tc2<E16, 2, 3>(q, ldq, k, ldk, v, ldv, key_mask, out, ldo, B, Sq, Sk, heads, dtype, stream);
-  if (Sq <= 96 && chunks == 3)
-    return launch_attention_tc2<E16, 3, 3>(q, ldq, k, ldk, v, ldv, key_mask, out, ldo, B, Sq, Sk, heads, dtype, stream);
-  if (Sq <= 96 && chunks == 5)
-    return launch_attention_tc2<E16, 5, 3>(q, ldq, k, ldk, v, ldv, key_mask, out, ldo, B, Sq, Sk, heads, dtype, stream);
-  if (Sq <= 96)
-    return launch_attention_tc2<E16, 0, 3>(q, ldq, k, ldk, v, ldv, key_mask, out, ldo, B, Sq, Sk, heads, dtype, stream);
-  return launch_attention_tc2<E16, 0, 4>(q, ldq, k, ldk, v, ldv, key_mask, out, ldo, B, Sq, Sk, heads, dtype, stream);
+  if (p1 != nullptr) {
+    // two-problem launches are built for the row-in-registers kernels of the LXMERT shapes and the generic ones
+    if (Sq <= 96 && chunks == 2) return launch_attention_tc2<E16, 2, 3, true>(p0, p1, heads, dtype, stream);
+    if (Sq <= 96 && chunks == 3) return launch_attention_tc2<E16, 3, 3, true>(p0, p1, heads, dtype, stream);
+    if (Sq <= 96) return launch_attention_tc2<E16, 0, 3, true>(p0, p1, heads, dtype, stream);
+    return launch_attention_tc2<E16, 0, 4, true>(p0, p1, heads, dtype, stream);
+  }
+  if (Sq <= 96 && chunks == 2) return launch_attention_tc2<E16, 2, 3, false>(p0, p1, heads, dtype, stream);
+  if (Sq <= 96 && chunks == 3) return launch_attention_tc2<E16, 3, 3, false>(p0, p1, heads, dtype, stream);
+  if (Sq <= 96 && chunks == 5) return launch_attention_tc2<E16, 5, 3, false>(p0, p1, heads, dtype, stream);
+  if (Sq <= 96) return launch_attention_tc2<E16, 0, 3, false>(p0, p1, heads, dtype, stream);
+  return launch_attention_tc2<E16, 0, 4, false>(p0, p1, heads, dtype, stream);
 }
 
 // Arguments are validated by mmr::attention (attention.cu); on top of those this path needs 16-byte aligned output rows.
@@ -554,9 +625,28 @@ bool attention_tc2_eligible(const void* out16, int64_t ldo) {
 mmr_status attention_tc2(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                          const int32_t* key_mask, void* out16, int64_t ldo, int B, int Sq, int Sk, int heads, int dtype,
                          cudaStream_t stream) {
-  if (dtype == MMR_DT_BF16)
-    return launch_attention_tc2_e<BF16>(q, ldq, k, ldk, v, ldv, key_mask, out16, ldo, B, Sq, Sk, heads, dtype, stream);
-  return launch_attention_tc2_e<FP16>(q, ldq, k, ldk, v, ldv, key_mask, out16, ldo, B, Sq, Sk, heads, dtype, stream);
+  const T2Problem p{q, k, v, ldq, ldk, ldv, key_mask, out16, ldo, B, Sq, Sk};
+  if (dtype == MMR_DT_BF16) return launch_attention_tc2_e<BF16>(p, nullptr, heads, dtype, stream);
+  return launch_attention_tc2_e<FP16>(p, nullptr, heads, dtype, stream);
+}
+
+// Two attention problems in ONE launch (see the kernel's comment on segments): what LXMERT issues back to back for its
+// two streams (modeling.py:381-391 per stream, :462-463 for the two directions of the shared cross-attention block).
+mmr_status attention_pair(const AttentionArgs& a, const AttentionArgs& b, int heads, int dtype, cudaStream_t stream) {
+  MMR_TRY(require_sm100());
+  for (const AttentionArgs* x : {&a, &b}) {
+    MMR_REQUIRE(x->q && x->k && x->v && x->out16 && x->B > 0, "attention_pair: null pointer or empty batch");
+    MMR_REQUIRE(x->Sq > 0 && x->Sq <= 128 && x->Sk > 0 && x->Sk <= 128, "attention_pair: Sq=%d Sk=%d must be in [1,128]",
+                x->Sq, x->Sk);
+    MMR_REQUIRE(x->ldq % 8 == 0 && x->ldk % 8 == 0 && x->ldv % 8 == 0 && x->ldo % 8 == 0 &&
+                    ((reinterpret_cast<uintptr_t>(x->q) | reinterpret_cast<uintptr_t>(x->k) |
+                      reinterpret_cast<uintptr_t>(x->v) | reinterpret_cast<uintptr_t>(x->out16)) & 15) == 0,
+                "attention_pair: operands and output rows must be 16-byte aligned");
+  }
+  const T2Problem p0{a.q, a.k, a.v, a.ldq, a.ldk, a.ldv, a.key_mask, a.out16, a.ldo, a.B, a.Sq, a.Sk};
+  const T2Problem p1{b.q, b.k, b.v, b.ldq, b.ldk, b.ldv, b.key_mask, b.out16, b.ldo, b.B, b.Sq, b.Sk};
+  if (dtype == MMR_DT_BF16) return launch_attention_tc2_e<BF16>(p0, &p1, heads, dtype, stream);
+  return launch_attention_tc2_e<FP16>(p0, &p1, heads, dtype, stream);
 }
 
 }  // namespace mmr

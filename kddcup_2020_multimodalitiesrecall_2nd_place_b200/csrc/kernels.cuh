@@ -25,6 +25,16 @@ bool attention_tc2_eligible(const void* out16, int64_t ldo);
 mmr_status attention_tc2(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                          const int32_t* key_mask, void* out16, int64_t ldo, int B, int Sq, int Sk, int heads, int dtype,
                          cudaStream_t stream);
+// two attention problems in one launch of the tcgen05 kernel (attention_tc2.cu)
+struct AttentionArgs {
+  const void *q, *k, *v;
+  int64_t ldq, ldk, ldv;
+  const int32_t* key_mask;
+  void* out16;
+  int64_t ldo;
+  int B, Sq, Sk;
+};
+mmr_status attention_pair(const AttentionArgs& a, const AttentionArgs& b, int heads, int dtype, cudaStream_t stream);
 mmr_status cast16(const float* x, void* out16, int64_t n, int dtype, cudaStream_t stream);
 // out = LN(A . W^T + bias + residual) for N = 768 in one kernel (gemm_ln_sm100.cu); residual may alias out32.
 bool gemm_ln_eligible(int M, int N, int K, int dtype);

@@ -13,6 +13,7 @@
 // stream, rows [B*Lq, B*(Lq+R)) the visual stream, so the weight-shared cross-attention block (modeling.py:462-463)
 // runs its QKV and output projections as single GEMMs over all rows.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <algorithm>
@@ -702,6 +703,25 @@ static mmr_status attend(Ctx& c, int64_t q0, int Sq, int64_t k0, int Sk, const i
                     Sq, Sk, c.h->cfg.heads, c.dt, c.st));
   return c.mark(K_ATTENTION, 4.0 * B * Sq * Sk * c.H);
 }
+// Two attention problems of one batch in ONE launch (LXMERT: both streams' self-attention, or both directions of the
+// shared cross-attention): saves a launch, a prologue and a tail of a kernel that is latency-bound at these shapes.
+static mmr_status attend2(Ctx& c, int64_t q0, int Sq0, int64_t k0, int Sk0, const int32_t* mask0, int64_t q1, int Sq1,
+                          int64_t k1, int Sk1, const int32_t* mask1, int B) {
+  static const bool env_off = [] { const char* e = getenv("MMR_LX_ATTN_PAIR"); return e != nullptr && atoi(e) == 0; }();
+  bool separate = tuning(MMR_TUNE_LX_MERGE) == 0 || env_off;   // (environment: A/B measurements only)
+#ifdef MMR_EXPERIMENTAL
+  separate = separate || tuning(MMR_TUNE_ATTN_TC) != 2;   // the older attention kernels take one problem per launch
+#endif
+  if (separate) {
+    MMR_TRY(attend(c, q0, Sq0, k0, Sk0, mask0, B));
+    return attend(c, q1, Sq1, k1, Sk1, mask1, B);
+  }
+  const int64_t ld = 3 * int64_t(c.H);
+  const AttentionArgs a{c.qkv(q0, 0), c.qkv(k0, 1), c.qkv(k0, 2), ld, ld, ld, mask0, c.ctx(q0), c.H, B, Sq0, Sk0};
+  const AttentionArgs b{c.qkv(q1, 0), c.qkv(k1, 1), c.qkv(k1, 2), ld, ld, ld, mask1, c.ctx(q1), c.H, B, Sq1, Sk1};
+  MMR_TRY(attention_pair(a, b, c.h->cfg.heads, c.dt, c.st));
+  return c.mark(K_ATTENTION, 4.0 * B * (double(Sq0) * Sk0 + double(Sq1) * Sk1) * c.H);
+}
 // x = LN(ctx . Wo^T + bo + x), in place on the residual stream
 static mmr_status out_proj_ln(Ctx& c, const AttBlock& A, int64_t row0, int rows) {
   return c.G_LN(c.ctx(row0), c.H, A.out, A.ln, row0, rows);
@@ -728,8 +748,7 @@ static mmr_status two_stream_att(Ctx& c, const AttBlock& A1, const AttBlock& A2,
                                  const int32_t* mask1, const int32_t* mask2) {
   const int nl = B * Lq, nv = B * R;
   MMR_TRY(c.G2(c.x16(0), c.H, A1.qkv, A2.qkv, nl + nv, nl, c.qkv(0, 0), 3 * c.H, MMR_ACT_NONE));
-  MMR_TRY(attend(c, 0, Lq, 0, Lq, mask1, B));
-  MMR_TRY(attend(c, nl, R, nl, R, mask2, B));
+  MMR_TRY(attend2(c, 0, Lq, 0, Lq, mask1, nl, R, nl, R, mask2, B));
   return c.G_LN2(c.ctx(0), c.H, A1.out, A2.out, A1.ln, A2.ln, nl + nv, nl);
 }
 static mmr_status two_stream_ffn(Ctx& c, const FfnBlock& F1, const FfnBlock& F2, int nl, int nv) {
@@ -886,8 +905,10 @@ static mmr_status forward_lxmert(Ctx& c, const mmr_inputs* in, int B, float* pro
     const XLayer& X = h->x_layers[xi];
     // cross attention both ways with ONE weight set, both from the pre-update streams (modeling.py:462-463)
     MMR_TRY(qkv_proj(c, X.cross.qkv, 0, nl + nv));
-    MMR_TRY(attend(c, 0, Lq, v0, R, in->visn_mask, B));
-    if (prune && xi + 1 == h->x_layers.size()) {
+    const bool last_pruned = prune && xi + 1 == h->x_layers.size();
+    if (last_pruned) MMR_TRY(attend(c, 0, Lq, v0, R, in->visn_mask, B));
+    else MMR_TRY(attend2(c, 0, Lq, v0, R, in->visn_mask, v0, R, 0, Lq, in->query_mask, B));
+    if (last_pruned) {
       // last cross layer: the pooler reads lang[:, 0] (modeling.py:925), so its visual half (cross attention into the
       // visual stream, visual self-attention and FFN, modeling.py:468-479) feeds nothing; the language half needs the
       // cross-attended language rows as keys / values of its self-attention, then only the [CLS] rows
@@ -895,7 +916,6 @@ static mmr_status forward_lxmert(Ctx& c, const mmr_inputs* in, int B, float* pro
       MMR_TRY(cls_tail_block(c, X.lang_self, X.lang_ffn, 0, B, Lq, in->query_mask));
       break;
     }
-    MMR_TRY(attend(c, v0, R, 0, Lq, in->query_mask, B));
     MMR_TRY(out_proj_ln(c, X.cross, 0, nl + nv));
     if (merge) {
       MMR_TRY(two_stream_att(c, X.lang_self, X.visn_self, B, Lq, R, in->query_mask, in->visn_mask));

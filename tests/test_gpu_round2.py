@@ -487,3 +487,33 @@ def test_cast16_saturates_instead_of_overflowing():
     assert torch.isfinite(y).all()
     assert y[0].item() == 65504.0 and y[1].item() == -65504.0 and y[3].item() == 65504.0 and y[4].item() == 3.0
     assert torch.isinf(ops.cast16(x, torch.bfloat16)).sum() == 0      # bf16 has fp32's range
+
+
+# ---------------------------------------------------------------------------------------------- two problems, one launch
+def test_lxmert_paired_attention_launch_is_bit_identical():
+    """LXMERT issues attention in pairs -- both streams' self-attention, both directions of the shared cross-attention
+    block -- and the tcgen05 kernel takes the two problems as two SEGMENTS of one launch (different Sq / Sk / mask /
+    output).  Same bits as two launches (the arithmetic of an item does not depend on what else the launch carries),
+    fewer launches, within tolerance of the oracle; 32 x 36 (3 key chunks for both) and 20 x 40 (2 vs 3 chunks: the
+    shorter segment's stage rows hold the longer one's stale keys behind a -inf mask)."""
+    from kddcup_2020_multimodalitiesrecall_2nd_place_b200 import _lib
+    lib = _lib.load()
+    for lq, nbox, B in ((32, 36, 16), (20, 40, 13), (16, 8, 16)):
+        cfg = ModelConfig(LXMERT, n_layers=3, n_r_layers=2, n_x_layers=2, lq=lq, nbox=nbox, vocab=2000)
+        w = synth.make_weights(cfg, seed=synth.SEED0 + 61)
+        inp = synth.make_inputs(cfg, B, seed=synth.SEED0 + 61, n_queries=2)
+        sc = _scorer(cfg, w, B)
+        try:
+            out, launches = {}, {}
+            for merged in (1, 0):
+                _lib.check(lib.mmr_set_tuning(_lib.TUNE_LX_MERGE, merged))
+                _lib.check(lib.mmr_set_tuning(_lib.TUNE_PRUNE_LAST, 0))     # every attention pair of the graph
+                out[merged], _ = _gpu(sc, inp)
+                launches[merged] = sc.launches_per_forward()
+            assert torch.equal(out[0], out[1]), (lq, nbox)
+            assert launches[1] < launches[0]
+            assert (out[1] - _oracle(cfg, w, inp)["probs"]).abs().max().item() <= TOL
+        finally:
+            _lib.check(lib.mmr_set_tuning(_lib.TUNE_LX_MERGE, 1))
+            _lib.check(lib.mmr_set_tuning(_lib.TUNE_PRUNE_LAST, 1))
+            sc.close()
