@@ -116,14 +116,23 @@ class FeedAssembler:
         self.label_table = np.zeros((top, cfg.label_len), np.int32)      # class id -> padded token ids
         self.known = np.zeros(top, bool)
         for cid, phrase in label_map.items():
-            self.label_table[cid] = _pad(tokenizer.convert_tokens_to_ids(tokenizer.tokenize(phrase)), cfg.label_len)
+            self.label_table[cid] = self._checked(_pad(tokenizer.convert_tokens_to_ids(tokenizer.tokenize(phrase)),
+                                                       cfg.label_len), phrase)
             self.known[cid] = True
+
+    def _checked(self, ids: List[int], text: str) -> List[int]:
+        """Token ids index the embedding table on the device: a vocab.txt with more entries than the bound checkpoint's
+        word_embeddings would be an out-of-bounds gather there, so it is refused here."""
+        if ids and (min(ids) < 0 or max(ids) >= self.cfg.vocab):
+            raise ValueError(f"token id {max(ids)} of {text!r} is outside the model's vocabulary ({self.cfg.vocab} rows): "
+                             f"vocab.txt does not belong to this checkpoint")
+        return ids
 
     def query_ids(self, query: str) -> List[int]:
         ids = self._q.get(query)
         if ids is None:
             text = query.replace("sen department of", "forest style") if self.sen2forest else query
-            ids = self.tok.convert_tokens_to_ids(["[CLS]"] + self.tok.tokenize(text) + ["[SEP]"])
+            ids = self._checked(self.tok.convert_tokens_to_ids(["[CLS]"] + self.tok.tokenize(text) + ["[SEP]"]), query)
             self._q[query] = ids
         return ids
 

@@ -23,7 +23,7 @@ QUERIES = ["women's leather shoes", "sen department of dress 女士", "kids wash
 
 def _vocab():
     k = json.load(open(os.path.join(GOLD, "tokenizer_kat.json"), encoding="utf-8"))
-    return {t: i for i, t in enumerate(k["vocab"])}
+    return {t: i for i, t in enumerate(dict.fromkeys(k["vocab"]))}      # (the KAT list repeats two tokens)
 
 
 def _write_tsv(path, n, seed=5):
@@ -41,7 +41,7 @@ def test_tsv_to_submission_through_three_models(tmp_path):
     tsv = str(tmp_path / "testB.tsv")
     lines = _write_tsv(tsv, n)
     assert drivers.read_tsv_lines(tsv) == lines                  # header skipped
-    shapes = dict(lq=20, nbox=10, vocab=len(vocab))
+    shapes = dict(lq=20, nbox=10, vocab=max(vocab.values()) + 1)
     cfgs = {ZK: ModelConfig(ZK, n_layers=2, **shapes), LDS: ModelConfig(LDS, n_layers=2, **shapes),
             LXMERT: ModelConfig(LXMERT, n_layers=2, n_r_layers=1, n_x_layers=1, **shapes)}
     scorers = {k: MatchScorer(c, synth.make_weights(c, seed=31, trained_like=True), device=0, max_batch=16)
@@ -95,7 +95,7 @@ def test_kdd_load_and_predict_from_pth(tmp_path):
     (tmp_path / "labels.txt").write_text("".join(f"{i}\t{p}\n" for i, p in LABELS.items()), encoding="utf-8")
     (tmp_path / "data" / "valid").mkdir(parents=True)
     lines = _write_tsv(str(tmp_path / "data" / "valid" / "valid.tsv"), 20, seed=9)
-    cfg = ModelConfig(LXMERT, n_layers=2, n_r_layers=1, n_x_layers=1, lq=23, nbox=10, vocab=len(vocab))
+    cfg = ModelConfig(LXMERT, n_layers=2, n_r_layers=1, n_x_layers=1, lq=23, nbox=10, vocab=max(vocab.values()) + 1)
     w = synth.make_weights(cfg, seed=41)
     torch.save({"module." + k: torch.from_numpy(v) for k, v in w.items()}, str(tmp_path / "BEST.pth"))
     kdd = KDD(str(tmp_path / "data"), str(tmp_path / "result"), str(tmp_path / "vocab.txt"), str(tmp_path / "labels.txt"),
