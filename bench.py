@@ -43,6 +43,7 @@ from kddcup_2020_multimodalitiesrecall_2nd_place_b200.config import (LDS, LXMERT
                                                                       flops_per_pair)
 
 BATCH = 256
+N_SETS = 3   # rotating resident input sets: 3 x 75.5 MB of fp32 features + ~220 MB of weights per step > the 126 MB L2
 METRIC = "pairs_scored_per_sec"
 UNIT = "pairs/s"
 
@@ -70,6 +71,20 @@ def workload_name(cfg, batch):
                 f"{cfg.lq} query tokens x {cfg.nbox} regions x {cfg.feat_dim}-d, batch={batch}")
     return (f"{cfg.n_layers}-layer ImageBert ({cfg.kind}), {cfg.lq} query tokens x {cfg.nbox} regions x "
             f"{cfg.feat_dim}-d, batch={batch}")
+
+
+def config_record(cfg, B, args, world, graphs=True):
+    """The `config` object of the JSON line: names the workload; identical for the GPU arm and the --impl reference arm."""
+    return {"workload": workload_name(cfg, B), "pairs_per_step_per_gpu": B,
+            "l2_policy": f"{N_SETS} rotating resident input sets (3 x 75.5 MB fp32 features) + 220 MB of "
+                         "weights streamed per step: working set larger than the 126 MB L2",
+            "flops_per_pair": flops_per_pair(cfg), "precision": args.precision,
+            "arithmetic": f"{args.dtype} MMA operands, fp32 accumulate / residual stream / LayerNorm / softmax",
+            "collective": "one NCCL all-gather of fp32 scores inside the timed region" if world > 1 else None,
+            "last_block": "keys / values for all rows, attention + projections + FFN for the [CLS] rows only "
+                          "(the poolers read sequence_output[:, 0]); FLOPs counted are the reference's",
+            "launch": ("forward replayed from CUDA graphs (one per rotating input set, captured before the "
+                       "warm-up steps)" if graphs else "eager launches")}
 
 
 # ---------------------------------------------------------------------------------------------- clocks
@@ -241,24 +256,30 @@ def time_cpu_port(cfg, weights, sample_pairs, steps, warmup):
 
 
 def run_reference(args, cfg, rank):
+    """The reference arm: the reference's own algorithm for this path on the host cores (the fp32 port: TF-1.12 / py2
+    cannot run), K steps after W warm-up steps, each step a bounded SAMPLE of the GPU arm's step (16 of its 256 pairs),
+    same metric / unit / config."""
     if rank != 0:
         return
     sample = 16
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     weights = synth.make_weights(cfg, seed=synth.SEED0)
     steps, warmup = max(1, args.steps), max(0, args.warmup)
     # keep the whole run within a few minutes: probe one step, then cap the step count
     pps, s_per_step, cores = time_cpu_port(cfg, weights, sample, 1, 1)
     budget_steps = max(1, int(150.0 / max(s_per_step, 1e-3)))
     steps_run = min(steps, budget_steps)
-    pps, s_per_step, cores = time_cpu_port(cfg, weights, sample, steps_run, min(warmup, 2))
+    warm_run = min(warmup, max(0, budget_steps // 4))
+    pps, s_per_step, cores = time_cpu_port(cfg, weights, sample, steps_run, warm_run)
     line = {
         "impl": "reference", "metric": METRIC, "value": pps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps_run,
-        "warmup": min(warmup, 2), "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": warm_run, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(cfg, args.batch), "sample_pairs_per_step": sample},
+        "config": config_record(cfg, args.batch, args, world),
         "cpu_baseline": {"value": pps, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} pairs per step of the same workload, fp32 PyTorch restatement of the "
-                                   f"reference graph (TF-1.12/py2 not runnable), {cores} threads"},
+                         "sample": f"{sample} pairs per step of the same workload ({args.batch} pairs per step on the GPU "
+                                   f"arm), fp32 PyTorch restatement of the reference graph (TF-1.12 / py2 not runnable), "
+                                   f"{cores} threads"},
         "e2e": {"value": pps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -310,8 +331,6 @@ class Env:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-
-N_SETS = 3   # rotating resident input sets: 3 x 75.5 MB of fp32 features + ~220 MB of weights per step > the 126 MB L2
 
 
 def resident_sets(sc, cfg, B, rank, dev):
@@ -679,16 +698,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": workload_name(cfg, B), "pairs_per_step_per_gpu": B,
-                       "l2_policy": f"{N_SETS} rotating resident input sets (3 x 75.5 MB fp32 features) + 220 MB of "
-                                    "weights streamed per step: working set larger than the 126 MB L2",
-                       "flops_per_pair": flops_per_pair(cfg), "precision": args.precision,
-                       "arithmetic": f"{args.dtype} MMA operands, fp32 accumulate / residual stream / LayerNorm / softmax",
-                       "collective": "one NCCL all-gather of fp32 scores inside the timed region" if world > 1 else None,
-                       "last_block": "keys / values for all rows, attention + projections + FFN for the [CLS] rows only "
-                                     "(the poolers read sequence_output[:, 0]); FLOPs counted are the reference's",
-                       "launch": ("forward replayed from CUDA graphs (one per rotating input set, captured before the "
-                                  "warm-up steps)" if sc.use_graphs else "eager launches")},
+            "config": config_record(cfg, B, args, world, sc.use_graphs),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "launches_per_forward": sc.launches_per_forward(),
             "roofline": roofline, "cpu_baseline": cpu, "other_models": other_models or None, "strict": strict,
             "cfg4": cfg4, "cfg5": cfg5,

@@ -85,7 +85,7 @@ cls_attention_kernel(const typename E16::T* __restrict__ q, int64_t q_pair_strid
   float o0 = 0.f, o1 = 0.f;
   const uint32_t* v32 = reinterpret_cast<const uint32_t*>(v + int64_t(b) * Sk * ldkv + h * kClsHeadDim) + lane;
   const int64_t ld32 = ldkv / 2;
-#pragma unroll 4
+#pragma unroll 8
   for (int j = 0; j < Sk; ++j) {
     const float2 vv = E16::unpack(__ldg(v32 + int64_t(j) * ld32));
     const float p = s_p[h][j];
