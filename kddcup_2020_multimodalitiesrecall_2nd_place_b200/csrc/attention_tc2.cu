@@ -439,7 +439,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           sum = sum0 + sum1;
         } else {
           // long rows (more than 80 keys): two passes over the S row in TMEM
-          float mx = -INFINITY;
+          float mx = -INFINITY, sum0 = 0.f, sum1 = 0.f;
           for (int c = 0; c < n_chunks; ++c) {
             uint32_t v[16];
             tmem_ld_32x16(tmem_s + uint32_t(c * 16), v);
@@ -465,12 +465,16 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
               const float e1 = ex2_approx(fmaf(__uint_as_float(v[4 * q + 1]), kScaleLog2e, mm.y) - mx);
               const float e2 = ex2_approx(fmaf(__uint_as_float(v[4 * q + 2]), kScaleLog2e, mm.z) - mx);
               const float e3 = ex2_approx(fmaf(__uint_as_float(v[4 * q + 3]), kScaleLog2e, mm.w) - mx);
-              sum += (e0 + e1) + (e2 + e3);
+              sum0 += e0;   // the same two running sums, in the same order, as the row-in-registers path: a row's bits do
+              sum1 += e1;   // not depend on which specialisation of the kernel a launch (or a paired launch) picks
+              sum0 += e2;
+              sum1 += e3;
               pk[2 * q] = E16::pack(e0, e1);
               pk[2 * q + 1] = E16::pack(e2, e3);
             }
             tmem_st_32x8(tmem_s + uint32_t(c * 8), pk);
           }
+          sum = sum0 + sum1;
         }
         tmem_st_wait();
         inv = 1.0f / sum;

@@ -335,10 +335,8 @@ def test_lxmert_two_stream_merged_launches(B, lq):
             out[merged], _ = _gpu_probs(sc, inp)
             launches[merged] = sc.launches_per_forward()
         assert torch.equal(out[0], out[1])
-        if (B * lq) % 256 == 0:
-            assert launches[1] < launches[0]
-        else:
-            assert launches[1] == launches[0]
+        # fewer launches either way: the GEMM merge needs a tile-aligned split, the paired cross-attention launch does not
+        assert launches[1] < launches[0]
         assert (out[1] - _oracle(cfg, w, inp)["probs"]).abs().max().item() <= TOL
     finally:
         _lib.check(lib.mmr_set_tuning(_lib.TUNE_LX_MERGE, 1))
