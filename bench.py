@@ -84,7 +84,11 @@ def config_record(cfg, B, args, world, graphs=True):
             "last_block": "keys / values for all rows, attention + projections + FFN for the [CLS] rows only "
                           "(the poolers read sequence_output[:, 0]); FLOPs counted are the reference's",
             "launch": ("forward replayed from CUDA graphs (one per rotating input set, captured before the "
-                       "warm-up steps)" if graphs else "eager launches")}
+                       "warm-up steps)" if graphs else "eager launches"),
+            "query_grouping": (f"LXMERT: the {cfg.n_layers} query-only language blocks run once per DISTINCT query of a "
+                               f"batch ({max(1, B // 30)} queries per {B} pairs, the testB ratio of ~30 candidates per "
+                               "query) and are expanded before the cross-modality blocks; FLOPs counted are the "
+                               "reference's, which evaluates them per pair") if cfg.kind == LXMERT else None}
 
 
 # ---------------------------------------------------------------------------------------------- clocks

@@ -102,10 +102,14 @@ int mmr_experimental_build(void);
  *                                                            FFN and both LayerNorms run for the B [CLS] rows alone (LXMERT:
  *                                                            the last cross layer's visual half, modeling.py:468-479, feeds
  *                                                            nothing and is skipped); 0 = the full last block.  Forced off
- *                                                            while mmr_set_debug_taps is non-zero (taps want every row). */
+ *                                                            while mmr_set_debug_taps is non-zero (taps want every row).
+ *   MMR_TUNE_LX_QUERY_DEDUP (env MMR_LX_QUERY_DEDUP, default 1) LXMERT: honour mmr_inputs.lang_unique / lang_slot (the
+ *                                                            language-only blocks once per distinct query of the batch);
+ *                                                            0 = ignore them.  Also off while debug taps are on. */
 enum { MMR_TUNE_GEMM_PAIR = 0, MMR_TUNE_GEMM_P16 = 1, MMR_TUNE_GEMM_TAIL = 2, MMR_TUNE_GEMM_CLUSTER = 3,
        MMR_TUNE_GEMM_LN = 4, MMR_TUNE_PDL = 5, MMR_TUNE_ATTN_TMA = 6, MMR_TUNE_ATTN_TC = 7, MMR_TUNE_LN_ROW_CFG = 8,
-       MMR_TUNE_LABEL_DEDUP = 9, MMR_TUNE_LX_MERGE = 10, MMR_TUNE_PRUNE_LAST = 11, MMR_TUNE_COUNT = 12 };
+       MMR_TUNE_LABEL_DEDUP = 9, MMR_TUNE_LX_MERGE = 10, MMR_TUNE_PRUNE_LAST = 11, MMR_TUNE_LX_QUERY_DEDUP = 12,
+       MMR_TUNE_COUNT = 13 };
 mmr_status mmr_set_tuning(int knob, int value);
 /* Current value of a knob (-1 for an unknown one). */
 int mmr_get_tuning(int knob);
@@ -297,6 +301,15 @@ typedef struct {
   const float* region_sum;    /* zk, optional: [B, nbox, hidden] fp32 = label + box + feat term ALREADY fused
                                  (the `imgfeat` argument of pixelbert.BertModel, pixelbert.py:150-186); when
                                  non-NULL, feats / boxes / label_ids are ignored                     */
+  /* lxmert, optional (ABI version 2): the language stream of LXMERT's first n_layers blocks depends on the QUERY only
+   * (modeling.py:577-578 runs them before any cross-attention), and a candidate set scores ~30 products per query.
+   * lang_unique [n_lang_unique] = ascending pair indices, one representative per distinct (query_ids, query_mask) row of
+   * the batch; lang_slot [B] = position in lang_unique of pair b's representative.  When given (and
+   * MMR_TUNE_LX_QUERY_DEDUP != 0) those blocks run on n_lang_unique rows instead of B and are expanded to all pairs
+   * before the cross-modality blocks: same scores, less work.  NULL / 0 = every pair computes its own.           */
+  const int32_t* lang_unique;
+  const int32_t* lang_slot;
+  int32_t n_lang_unique;
 } mmr_inputs;
 
 mmr_status mmr_create(const mmr_config* cfg, const mmr_tensor* weights, int n_weights, int device,

@@ -11,7 +11,7 @@ MMR_OK = 0
 DT_FP16, DT_BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_GELU_TANH, ACT_GELU_ERF, ACT_TANH = range(5)
 MODEL_ZK, MODEL_LDS, MODEL_LXMERT = range(3)
-TUNE_GEMM_PAIR, TUNE_GEMM_P16, TUNE_GEMM_TAIL, TUNE_GEMM_CLUSTER, TUNE_GEMM_LN, TUNE_PDL, TUNE_ATTN_TMA, TUNE_ATTN_TC, TUNE_LN_ROW_CFG, TUNE_LABEL_DEDUP, TUNE_LX_MERGE, TUNE_PRUNE_LAST = range(12)
+TUNE_GEMM_PAIR, TUNE_GEMM_P16, TUNE_GEMM_TAIL, TUNE_GEMM_CLUSTER, TUNE_GEMM_LN, TUNE_PDL, TUNE_ATTN_TMA, TUNE_ATTN_TC, TUNE_LN_ROW_CFG, TUNE_LABEL_DEDUP, TUNE_LX_MERGE, TUNE_PRUNE_LAST, TUNE_LX_QUERY_DEDUP = range(13)
 PRECISION_FAST, PRECISION_STRICT = 0, 1
 
 # every symbol include/mmrecall.h declares (tests check the .so exports all of them)
@@ -36,7 +36,7 @@ class MmrTensor(C.Structure):
 class MmrInputs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "query_ids", "segment_ids", "label_ids", "feats", "boxes", "len_query", "num_boxes", "query_mask",
-        "visn_mask", "labels", "region_sum")]
+        "visn_mask", "labels", "region_sum", "lang_unique", "lang_slot")] + [("n_lang_unique", C.c_int32)]
 
 
 class MmrError(RuntimeError):

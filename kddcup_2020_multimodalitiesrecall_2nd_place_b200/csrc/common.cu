@@ -24,7 +24,7 @@ static bool g_tuning_init = false;
 static unsigned g_tuning_generation = 0;   // bumped by mmr_set_tuning: captured CUDA graphs of a forward are keyed on it
 static void tuning_init() {
   static const struct { const char* env; int def; } spec[MMR_TUNE_COUNT] = {
-      {"MMR_GEMM_PAIR", 1}, {"MMR_GEMM_P16", 1}, {"MMR_GEMM_TAIL", 1}, {"MMR_GEMM_CLUSTER", 1}, {"MMR_GEMM_LN", 1}, {"MMR_PDL", 1}, {"MMR_ATTN_TMA", 0}, {"MMR_ATTN_TC", 2}, {"MMR_LN_ROW_CFG", 0}, {"MMR_LABEL_DEDUP", 1}, {"MMR_LX_MERGE", 1}, {"MMR_PRUNE_LAST", 1}};
+      {"MMR_GEMM_PAIR", 1}, {"MMR_GEMM_P16", 1}, {"MMR_GEMM_TAIL", 1}, {"MMR_GEMM_CLUSTER", 1}, {"MMR_GEMM_LN", 1}, {"MMR_PDL", 1}, {"MMR_ATTN_TMA", 0}, {"MMR_ATTN_TC", 2}, {"MMR_LN_ROW_CFG", 0}, {"MMR_LABEL_DEDUP", 1}, {"MMR_LX_MERGE", 1}, {"MMR_PRUNE_LAST", 1}, {"MMR_LX_QUERY_DEDUP", 1}};
   for (int i = 0; i < MMR_TUNE_COUNT; ++i) {
     const char* e = getenv(spec[i].env);
     g_tuning[i] = e ? atoi(e) : spec[i].def;

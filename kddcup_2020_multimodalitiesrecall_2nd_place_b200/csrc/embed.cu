@@ -333,22 +333,53 @@ lds_embed_kernel(const int32_t* __restrict__ query_ids, const int32_t* __restric
 // lang0 = LN(E[q] + Pos[s] + Ttype[0])  (modeling.py:283-297)
 template <class E16>
 __global__ void __launch_bounds__(256)
-lx_lang_embed_kernel(const int32_t* __restrict__ query_ids, const float* __restrict__ E,
-                     const float* __restrict__ T, const float* __restrict__ P, const float* __restrict__ gamma,
-                     const float* __restrict__ beta, int Lq, int rows, typename E16::T* __restrict__ x16,
-                     float* __restrict__ x32) {
+lx_lang_embed_kernel(const int32_t* __restrict__ query_ids, const int32_t* __restrict__ pair_map,
+                     const float* __restrict__ E, const float* __restrict__ T, const float* __restrict__ P,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, int Lq, int rows,
+                     typename E16::T* __restrict__ x16, float* __restrict__ x32) {
   pdl_wait();
   pdl_launch_dependents();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const int s = row % Lq;
+  // output row group u embeds the query of pair pair_map[u] (one row group per DISTINCT query), or of pair u itself
+  const int src_pair = pair_map != nullptr ? __ldg(pair_map + row / Lq) : row / Lq;
   Row x;
-  row_load(x, E + int64_t(__ldg(query_ids + row)) * kH, lane);
+  row_load(x, E + int64_t(__ldg(query_ids + int64_t(src_pair) * Lq + s)) * kH, lane);
   row_add(x, P + int64_t(s) * kH, lane);
   row_add(x, T, lane);
   row_layernorm(x, gamma, beta, lane);
   row_store<E16>(x, x16 + int64_t(row) * kH, x32 + int64_t(row) * kH, lane);
+}
+
+// Language stream computed once per distinct query (mmr_inputs.lang_unique / lang_slot): the compact key mask of the
+// representatives, and the expansion of the compact stream to all pairs before the cross-modality blocks.
+__global__ void __launch_bounds__(256)
+lx_gather_mask_kernel(const int32_t* __restrict__ mask, const int32_t* __restrict__ pair_map, int Lq, int n,
+                      int32_t* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __ldg(mask + int64_t(__ldg(pair_map + i / Lq)) * Lq + i % Lq);
+}
+template <class E16>
+__global__ void __launch_bounds__(256)
+lx_expand_rows_kernel(const float* __restrict__ src32, const typename E16::T* __restrict__ src16,
+                      const int32_t* __restrict__ slot, int Lq, int rows, float* __restrict__ dst32,
+                      typename E16::T* __restrict__ dst16) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t src = int64_t(__ldg(slot + row / Lq)) * Lq + row % Lq;
+#pragma unroll
+  for (int i = 0; i < kNV; ++i) {
+    const int c = col_of(i, lane);
+    *reinterpret_cast<float4*>(dst32 + int64_t(row) * kH + c) = __ldg(reinterpret_cast<const float4*>(src32 + src * kH + c));
+    *reinterpret_cast<uint2*>(dst16 + int64_t(row) * kH + c) = __ldg(reinterpret_cast<const uint2*>(src16 + src * kH + c));
+  }
 }
 
 // z[b,r,:] = bconv + sum_t wconv[t] * LN(E[id_t] + Pos[t] + Ttype[0])   (modeling.py:915, 526-527)
@@ -580,10 +611,25 @@ mmr_status lds_embed(const int32_t* query_ids, const int32_t* segment_ids, const
 
 mmr_status lx_lang_embed(const int32_t* query_ids, const float* E, const float* T, const float* P,
                          const float* gamma, const float* beta, int Lq, int B, void* x16, float* x32, int dtype,
-                         cudaStream_t st) {
-  const int rows = B * Lq;
+                         cudaStream_t st, const int32_t* pair_map) {
+  const int rows = B * Lq;   // B = row groups written (distinct queries when pair_map is given)
   MMR_DISPATCH16(dtype, ((void)launch_pdl(lx_lang_embed_kernel<E16>, dim3(blocks_for(rows)), dim3(256), 0, st, 
-                            query_ids, E, T, P, gamma, beta, Lq, rows, static_cast<typename E16::T*>(x16), x32)));
+                            query_ids, pair_map, E, T, P, gamma, beta, Lq, rows, static_cast<typename E16::T*>(x16), x32)));
+  MMR_CUDA_OK(cudaGetLastError());
+  return MMR_OK;
+}
+mmr_status lx_gather_mask(const int32_t* mask, const int32_t* pair_map, int Lq, int U, int32_t* out, cudaStream_t st) {
+  const int n = U * Lq;
+  (void)launch_pdl(lx_gather_mask_kernel, dim3((n + 255) / 256), dim3(256), 0, st, mask, pair_map, Lq, n, out);
+  MMR_CUDA_OK(cudaGetLastError());
+  return MMR_OK;
+}
+mmr_status lx_expand_rows(const float* src32, const void* src16, const int32_t* slot, int Lq, int B, float* dst32,
+                          void* dst16, int dtype, cudaStream_t st) {
+  const int rows = B * Lq;
+  MMR_DISPATCH16(dtype, ((void)launch_pdl(lx_expand_rows_kernel<E16>, dim3(blocks_for(rows)), dim3(256), 0, st, src32,
+                            static_cast<const typename E16::T*>(src16), slot, Lq, rows, dst32,
+                            static_cast<typename E16::T*>(dst16))));
   MMR_CUDA_OK(cudaGetLastError());
   return MMR_OK;
 }

@@ -169,6 +169,10 @@ struct mmr_handle {
   float* lab_term32 = nullptr;
   float* layer_tap = nullptr;   // [n_layers, rows_max, hidden], allocated by mmr_set_debug_taps(h, 2)
   int32_t* key_mask = nullptr;
+  // lxmert: compact language stream, one row group per distinct query (mmr_inputs.lang_unique), and its key mask
+  void* xl16c = nullptr;
+  float* xl32c = nullptr;
+  int32_t* lang_mask_c = nullptr;
   // [CLS]-row tail of the last block (MMR_TUNE_PRUNE_LAST): compact [B, .] buffers
   void *xc16 = nullptr, *ctxc16 = nullptr, *hc16 = nullptr;
   float* xc32 = nullptr;
@@ -576,6 +580,11 @@ static mmr_status alloc_workspace(mmr_handle* h) {
     h->emb_tap = static_cast<float*>(take(M * H * 4));
     h->xc16 = take(B * H * 2);
     h->xc32 = static_cast<float*>(take(B * H * 4));
+    if (c.model_kind == MMR_MODEL_LXMERT && !strict) {
+      h->xl16c = take(B * c.lq * H * 2);
+      h->xl32c = static_cast<float*>(take(B * c.lq * H * 4));
+      h->lang_mask_c = static_cast<int32_t*>(take(B * c.lq * 4));
+    }
     void* ln_mem = take(ln_bytes);
     if (zk) {
       h->lab_tab = static_cast<unsigned long long*>(take(size_t(lab_slots) * 8));
@@ -618,8 +627,12 @@ struct Ctx {
   int dt;
   int H;
   int launches = 0;
-  uint8_t* x16(int64_t row) const { return static_cast<uint8_t*>(h->x16) + row * H * 2; }
-  float* x32(int64_t row) const { return h->x32 + row * H; }
+  // the residual stream the block helpers below work on: the handle's x16 / x32, or (LXMERT, language blocks once per
+  // distinct query) the compact language stream
+  void* x16_base = nullptr;
+  float* x32_base = nullptr;
+  uint8_t* x16(int64_t row) const { return static_cast<uint8_t*>(x16_base ? x16_base : h->x16) + row * H * 2; }
+  float* x32(int64_t row) const { return (x32_base ? x32_base : h->x32) + row * H; }
   uint8_t* qkv(int64_t row, int part) const {
     return static_cast<uint8_t*>(h->qkv16) + (row * 3 * H + int64_t(part) * H) * 2;
   }
@@ -871,9 +884,20 @@ static mmr_status forward_lxmert(Ctx& c, const mmr_inputs* in, int B, float* pro
               "mmr_forward(lxmert): missing input pointer");
   const int64_t v0 = int64_t(B) * Lq;  // first visual row
   const int nl = B * Lq, nv = B * R;
+  // Language blocks once per distinct query of the batch (mmr_inputs.lang_unique / lang_slot): U row groups instead of B.
+  const int U = (tuning(MMR_TUNE_LX_QUERY_DEDUP) != 0 && h->keep_taps == 0 && in->lang_unique != nullptr &&
+                 in->lang_slot != nullptr && in->n_lang_unique > 0 && in->n_lang_unique < B && !h->layers.empty())
+                    ? in->n_lang_unique : 0;
   // language embedding (modeling.py:913)
-  MMR_TRY(lx_lang_embed(in->query_ids, h->E, h->T, h->P, h->emb_ln.gamma, h->emb_ln.beta, Lq, B, c.x16(0), c.x32(0),
-                        c.dt, c.st));
+  if (U > 0) {
+    MMR_TRY(lx_lang_embed(in->query_ids, h->E, h->T, h->P, h->emb_ln.gamma, h->emb_ln.beta, Lq, U, h->xl16c, h->xl32c, c.dt,
+                          c.st, in->lang_unique));
+    MMR_TRY(c.mark(K_ROW, 0));
+    MMR_TRY(lx_gather_mask(in->query_mask, in->lang_unique, Lq, U, h->lang_mask_c, c.st));
+  } else {
+    MMR_TRY(lx_lang_embed(in->query_ids, h->E, h->T, h->P, h->emb_ln.gamma, h->emb_ln.beta, Lq, B, c.x16(0), c.x32(0),
+                          c.dt, c.st));
+  }
   MMR_TRY(c.mark(K_ROW, 0));
   // visual embedding (modeling.py:519-533): (LN(fc(f)) + LN(fc(box)) + LN(fc(conv(label_emb)))) / 3
   const float third = 1.0f / 3.0f;
@@ -893,13 +917,25 @@ static mmr_status forward_lxmert(Ctx& c, const mmr_inputs* in, int B, float* pro
   // language layers (modeling.py:577-578) and visual layers (:582-583) are independent chains: the first
   // min(9, 5) of each run pairwise through merged launches, the rest alone
   const bool merge = tuning(MMR_TUNE_LX_MERGE) != 0 && nl % 256 == 0;
-  const size_t n_both = merge ? std::min(h->layers.size(), h->r_layers.size()) : 0;
+  if (U > 0) {
+    // the language-only blocks (modeling.py:577-578) on the compact stream, the visual ones (:582-583) on theirs, then
+    // every pair receives its query's rows
+    Ctx cl = c;
+    cl.x16_base = h->xl16c;
+    cl.x32_base = h->xl32c;
+    for (const Layer& L : h->layers) MMR_TRY(bert_layer(cl, L, 0, U, Lq, h->lang_mask_c));
+    c.launches = cl.launches;
+    for (const Layer& L : h->r_layers) MMR_TRY(bert_layer(c, L, v0, B, R, in->visn_mask));
+    MMR_TRY(lx_expand_rows(h->xl32c, h->xl16c, in->lang_slot, Lq, B, c.x32(0), c.x16(0), c.dt, c.st));
+    MMR_TRY(c.mark(K_ROW, 0));
+  }
+  const size_t n_both = (merge && U == 0) ? std::min(h->layers.size(), h->r_layers.size()) : 0;
   for (size_t i = 0; i < n_both; ++i) {
     MMR_TRY(two_stream_att(c, h->layers[i].att, h->r_layers[i].att, B, Lq, R, in->query_mask, in->visn_mask));
     MMR_TRY(two_stream_ffn(c, h->layers[i].ffn, h->r_layers[i].ffn, nl, nv));
   }
-  for (size_t i = n_both; i < h->layers.size(); ++i) MMR_TRY(bert_layer(c, h->layers[i], 0, B, Lq, in->query_mask));
-  for (size_t i = n_both; i < h->r_layers.size(); ++i) MMR_TRY(bert_layer(c, h->r_layers[i], v0, B, R, in->visn_mask));
+  for (size_t i = n_both; U == 0 && i < h->layers.size(); ++i) MMR_TRY(bert_layer(c, h->layers[i], 0, B, Lq, in->query_mask));
+  for (size_t i = n_both; U == 0 && i < h->r_layers.size(); ++i) MMR_TRY(bert_layer(c, h->r_layers[i], v0, B, R, in->visn_mask));
   const bool prune = prune_last(h);
   for (size_t xi = 0; xi < h->x_layers.size(); ++xi) {                                        // :589-591
     const XLayer& X = h->x_layers[xi];

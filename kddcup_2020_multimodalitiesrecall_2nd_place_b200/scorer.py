@@ -50,6 +50,21 @@ def feed_spec(cfg: ModelConfig) -> Dict[str, tuple]:
     return {k: spec[k] for k in _FEEDS[cfg.kind]}
 
 
+def distinct_queries(query_ids, query_mask):
+    """LXMERT's first `n_layers` blocks see the query only (lxrt/modeling.py:577-578), and a candidate set scores ~30
+    products per query: (lang_unique [U] int32 ascending representative pair indices, lang_slot [B] int32 position of
+    every pair's representative in lang_unique) of a batch, for mmr_inputs.lang_unique / lang_slot.  Host arithmetic on
+    [B, lq] integers."""
+    q = query_ids.numpy() if torch.is_tensor(query_ids) else np.asarray(query_ids)
+    m = query_mask.numpy() if torch.is_tensor(query_mask) else np.asarray(query_mask)
+    key = np.concatenate([q.astype(np.int64), m.astype(np.int64)], axis=1)
+    _, first, inverse = np.unique(key, axis=0, return_index=True, return_inverse=True)
+    order = np.argsort(first, kind="stable")              # representatives in ascending pair order
+    rank = np.empty_like(order)
+    rank[order] = np.arange(len(order))
+    return (torch.from_numpy(first[order].astype(np.int32)), torch.from_numpy(rank[inverse.reshape(-1)].astype(np.int32)))
+
+
 class MatchScorer:
     """One model (zk / lds / lxmert) resident on one B200."""
 
@@ -95,6 +110,9 @@ class MatchScorer:
         # +2 % on the 12-layer forward).  mmr_forward neither allocates nor synchronises and keeps its state on the
         # device, which is what makes the replay exact (tests/test_gpu_parity.py).  MMR_CUDA_GRAPHS=0 turns it off.
         self.use_graphs = os.environ.get("MMR_CUDA_GRAPHS", "1") != "0"
+        # LXMERT: evaluate the query-only language blocks once per distinct query of a batch (mmr_inputs.lang_unique);
+        # to_feeds / score_stream derive the grouping from the host copies of query_ids / query_mask
+        self.dedup_queries = cfg.kind == LXMERT
         self._graphs, self._seen = {}, set()
         self._capture_stream = None
         self._taps_on = self._profiling_on = False
@@ -139,6 +157,14 @@ class MatchScorer:
                     or not fused.is_contiguous():
                 raise ValueError("feed 'region_sum': need contiguous float32 [B, nbox, hidden]")
             inp.region_sum = fused.data_ptr()
+        n_unique = 0
+        if self.cfg.kind == LXMERT and feeds.get("lang_unique") is not None and feeds.get("lang_slot") is not None:
+            lu, ls = feeds["lang_unique"], feeds["lang_slot"]
+            if lu.dtype != torch.int32 or ls.dtype != torch.int32 or tuple(ls.shape) != (B,) or lu.dim() != 1 \
+                    or not (0 < lu.shape[0] <= B) or not lu.is_cuda or not ls.is_cuda:
+                raise ValueError("feeds 'lang_unique' [U] / 'lang_slot' [B]: need int32 device tensors, 0 < U <= B")
+            n_unique = int(lu.shape[0])
+            inp.lang_unique, inp.lang_slot, inp.n_lang_unique = lu.data_ptr(), ls.data_ptr(), n_unique
         caller_owns_output = probs_out is not None
         if probs_out is None:
             probs_out = torch.empty((B, 2), dtype=torch.float32, device=self.device)
@@ -153,7 +179,7 @@ class MatchScorer:
                 or torch.cuda.is_current_stream_capturing():
             launch()
             return probs_out
-        key = (B, int(self.lib.mmr_tuning_generation()), probs_out.data_ptr(),
+        key = (B, n_unique, int(self.lib.mmr_tuning_generation()), probs_out.data_ptr(),
                0 if logits_out is None else logits_out.data_ptr(), 0 if pooled_out is None else pooled_out.data_ptr(),
                tuple(int(getattr(inp, f[0]) or 0) for f in inp._fields_))
         g = self._graphs.get(key)
@@ -225,6 +251,8 @@ class MatchScorer:
                     raise ValueError(f"feed '{name}': ids must lie in [0, {limits[name]}), got [{lo}, {hi}]")
             t = t.to(dt).contiguous()
             out[name] = t if t.is_pinned() else t.pin_memory()
+        if self.cfg.kind == LXMERT and self.dedup_queries and out["query_ids"].shape[0] > 1:
+            out["lang_unique"], out["lang_slot"] = distinct_queries(out["query_ids"], out["query_mask"])
         return out
 
     def _make_slots(self):
@@ -233,6 +261,9 @@ class MatchScorer:
             self._slots = []
             for _ in range(2):
                 dev = {n: torch.empty((Bm, *shape), dtype=dt, device=self.device) for n, (dt, shape) in self.spec.items()}
+                if self.cfg.kind == LXMERT:
+                    dev["lang_unique"] = torch.empty((Bm,), dtype=torch.int32, device=self.device)
+                    dev["lang_slot"] = torch.empty((Bm,), dtype=torch.int32, device=self.device)
                 self._slots.append({"dev": dev, "free": torch.cuda.Event(), "ready": torch.cuda.Event(),
                                     "probs": torch.empty((Bm, 2), dtype=torch.float32, device=self.device)})
             self._copy_stream = torch.cuda.Stream(self.device)
@@ -275,15 +306,28 @@ class MatchScorer:
             if i >= 2:
                 s["ready"].synchronize()                  # H2D of chunk i-2 done: its source buffers may be rewritten
             chunk = fetch(lo, hi)
+            group = None
+            if self.cfg.kind == LXMERT and self.dedup_queries and hi - lo > 1 and not chunk["query_ids"].is_cuda \
+                    and not chunk["query_mask"].is_cuda:
+                group = [t.pin_memory() for t in distinct_queries(chunk["query_ids"], chunk["query_mask"])]
             with torch.cuda.stream(copy):
                 if i >= 2:
                     copy.wait_event(s["free"])            # kernels of chunk i-2 have consumed this slot
                 for name in self.spec:
                     s["dev"][name][: hi - lo].copy_(chunk[name], non_blocking=True)
+                if group is not None:
+                    s["dev"]["lang_unique"][: group[0].shape[0]].copy_(group[0], non_blocking=True)
+                    s["dev"]["lang_slot"][: hi - lo].copy_(group[1], non_blocking=True)
                 s["ready"].record(copy)
             compute.wait_event(s["ready"])
             # into the slot's own probs buffer: the forward then sees the same pointers every other chunk (graph replay)
-            self.forward_device({n: s["dev"][n][: hi - lo] for n in self.spec}, probs_out=s["probs"][: hi - lo])
+            dev_feeds = {n: s["dev"][n][: hi - lo] for n in self.spec}
+            if group is not None:
+                dev_feeds["lang_unique"] = s["dev"]["lang_unique"][: group[0].shape[0]]
+                dev_feeds["lang_slot"] = s["dev"]["lang_slot"][: hi - lo]
+                s.setdefault("keep", []).append(group)    # pinned sources stay alive until the copy has run
+                del s["keep"][:-2]
+            self.forward_device(dev_feeds, probs_out=s["probs"][: hi - lo])
             dev_probs[lo:hi].copy_(s["probs"][: hi - lo], non_blocking=True)
             s["free"].record(compute)
         out.copy_(dev_probs, non_blocking=True)

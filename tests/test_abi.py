@@ -30,7 +30,7 @@ def test_library_loads_and_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.MmrConfig) == 17 * 4
-    assert ctypes.sizeof(_lib.MmrInputs) == 11 * ctypes.sizeof(ctypes.c_void_p)
+    assert ctypes.sizeof(_lib.MmrInputs) == 14 * ctypes.sizeof(ctypes.c_void_p)   # 13 pointers + int32 (padded)
     assert ctypes.sizeof(_lib.MmrTensor) == 8 + 8 + 8 + 4 * 8   # name, data, ndim (+pad), dims[4]
 
 

@@ -169,7 +169,7 @@ def test_baseline_size_properties(kind):
     w = synth.make_weights(cfg, seed=synth.SEED0 + 2)
     inp = synth.make_inputs(cfg, B, seed=synth.SEED0 + 2)
     sc = _scorer(cfg, w, B)
-    feeds = {k: v.cuda() for k, v in sc.to_feeds(inp).items()}
+    feeds = {k: v.cuda() for k, v in sc.to_feeds(inp).items() if k in sc.spec}   # (no per-batch query grouping: sliced below)
     full = sc.forward_device(feeds).clone()
     halves = torch.cat([sc.forward_device({k: v[:128] for k, v in feeds.items()}).clone(),
                         sc.forward_device({k: v[128:] for k, v in feeds.items()}).clone()])

@@ -517,3 +517,47 @@ def test_lxmert_paired_attention_launch_is_bit_identical():
             _lib.check(lib.mmr_set_tuning(_lib.TUNE_LX_MERGE, 1))
             _lib.check(lib.mmr_set_tuning(_lib.TUNE_PRUNE_LAST, 1))
             sc.close()
+
+
+# ---------------------------------------------------------------------------------------------- language stream once per query
+@pytest.mark.parametrize("B,nq,full", [(60, 2, False), (256, 9, True), (17, 17, False), (33, 1, False)])
+def test_lxmert_language_blocks_once_per_distinct_query(B, nq, full):
+    """LXMERT's first n_layers blocks depend on the query only (modeling.py:577-578): with mmr_inputs.lang_unique /
+    lang_slot they run once per distinct query of the batch and are expanded before the cross-modality blocks.  Same
+    scores as every pair computing its own (bit-identical where both paths take the same kernels: more than 128 compact
+    rows), within tolerance of the oracle; a batch of all-distinct queries takes the ordinary path; the host path
+    (score: chunks of max_batch, grouping per chunk) agrees with the device path."""
+    from kddcup_2020_multimodalitiesrecall_2nd_place_b200 import _lib
+    from kddcup_2020_multimodalitiesrecall_2nd_place_b200.scorer import distinct_queries
+    lib = _lib.load()
+    cfg = _full_cfg(LXMERT, vocab=3000) if full else ModelConfig(LXMERT, n_layers=3, n_r_layers=2, n_x_layers=2, lq=32,
+                                                                  nbox=36, vocab=2000)
+    w = synth.make_weights(cfg, seed=synth.SEED0 + 71)
+    inp = synth.make_inputs(cfg, B, seed=synth.SEED0 + 71, n_queries=nq)
+    uniq, slot = distinct_queries(inp["query_ids"], inp["query_mask"])
+    assert len(uniq) <= nq and (inp["query_ids"][uniq.numpy()[slot.numpy()]] == inp["query_ids"]).all()
+    sc = _scorer(cfg, w, B)
+    try:
+        out, launches = {}, {}
+        for dedup in (1, 0):
+            _lib.check(lib.mmr_set_tuning(_lib.TUNE_LX_QUERY_DEDUP, dedup))
+            out[dedup], _ = _gpu(sc, inp)
+            launches[dedup] = sc.launches_per_forward()
+        d = (out[0] - out[1]).abs().max().item()
+        print(f"lxmert B={B}, {len(uniq)} distinct queries: dedup vs per-pair max|dscore| = {d:.2e}; launches "
+              f"{launches[1]} vs {launches[0]}")
+        if len(uniq) * cfg.lq > 128 and len(uniq) < B:
+            assert torch.equal(out[0], out[1])
+        assert d <= 4e-4
+        if not full:
+            assert (out[1] - _oracle(cfg, w, inp)["probs"]).abs().max().item() <= TOL
+        host = sc.to_feeds(inp)
+        small = _scorer(cfg, w, 16)
+        try:
+            got = small.score(host)                               # ragged chunks, grouping recomputed per chunk
+        finally:
+            small.close()
+        assert (got - out[1]).abs().max().item() <= 4e-4
+    finally:
+        _lib.check(lib.mmr_set_tuning(_lib.TUNE_LX_QUERY_DEDUP, 1))
+        sc.close()
