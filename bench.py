@@ -555,7 +555,11 @@ def run_cfg4(env, sc, cfg):
     from kddcup_2020_multimodalitiesrecall_2nd_place_b200.scorer import sharded_score_stream
     block = candidate_block(sc, cfg, synth.SEED0 + 404)
     fetch = block_fetch(block)
-    sharded_score_stream(sc, 4 * 256 * env.world, fetch, env.rank, env.world)          # warm-up (graphs, NCCL)
+    # warm-up = the workload itself, twice: MatchScorer runs a (batch, buffers) combination eagerly the first time it
+    # sees it and captures it into a CUDA graph the second time; the timed pass then replays, as any pass of a long
+    # scoring job after its first two does (a capture costs ~15 ms, a ragged tail chunk per rank stays cheap)
+    for _ in range(2):
+        sharded_score_stream(sc, CFG4_PAIRS, fetch, env.rank, env.world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     env.barrier()
     t0 = time.perf_counter()
@@ -583,8 +587,9 @@ def run_cfg5(env, scorers, cfgs):
     from kddcup_2020_multimodalitiesrecall_2nd_place_b200 import ensemble
     from kddcup_2020_multimodalitiesrecall_2nd_place_b200.scorer import sharded_score_stream
     fetchers = {k: block_fetch(candidate_block(scorers[k], cfgs[k], synth.SEED0 + 505)) for k in scorers}
-    for k, sc in scorers.items():
-        sharded_score_stream(sc, 2 * 256 * env.world, fetchers[k], env.rank, env.world)
+    for _ in range(2):                                        # warm-up = the workload itself, twice (see run_cfg4)
+        for k, sc in scorers.items():
+            sharded_score_stream(sc, CFG5_PAIRS, fetchers[k], env.rank, env.world)
     per_q = CFG5_PAIRS // CFG5_QUERIES
     qi = np.arange(CFG5_PAIRS, dtype=np.int64) // per_q
     pi = np.arange(CFG5_PAIRS, dtype=np.int64) % 6000           # products recur across queries: the filter has work

@@ -261,10 +261,12 @@ class MatchScorer:
             self._slots = []
             for _ in range(2):
                 dev = {n: torch.empty((Bm, *shape), dtype=dt, device=self.device) for n, (dt, shape) in self.spec.items()}
+                host = {}
                 if self.cfg.kind == LXMERT:
-                    dev["lang_unique"] = torch.empty((Bm,), dtype=torch.int32, device=self.device)
-                    dev["lang_slot"] = torch.empty((Bm,), dtype=torch.int32, device=self.device)
-                self._slots.append({"dev": dev, "free": torch.cuda.Event(), "ready": torch.cuda.Event(),
+                    for n in ("lang_unique", "lang_slot"):
+                        dev[n] = torch.empty((Bm,), dtype=torch.int32, device=self.device)
+                        host[n] = torch.empty((Bm,), dtype=torch.int32).pin_memory()
+                self._slots.append({"dev": dev, "host": host, "free": torch.cuda.Event(), "ready": torch.cuda.Event(),
                                     "probs": torch.empty((Bm, 2), dtype=torch.float32, device=self.device)})
             self._copy_stream = torch.cuda.Stream(self.device)
         return self._slots
@@ -309,7 +311,11 @@ class MatchScorer:
             group = None
             if self.cfg.kind == LXMERT and self.dedup_queries and hi - lo > 1 and not chunk["query_ids"].is_cuda \
                     and not chunk["query_mask"].is_cuda:
-                group = [t.pin_memory() for t in distinct_queries(chunk["query_ids"], chunk["query_mask"])]
+                # (the slot's pinned staging tensors: reusable, the copies that read them two chunks ago have completed)
+                uniq, slot_of = distinct_queries(chunk["query_ids"], chunk["query_mask"])
+                s["host"]["lang_unique"][: uniq.shape[0]].copy_(uniq)
+                s["host"]["lang_slot"][: hi - lo].copy_(slot_of)
+                group = (s["host"]["lang_unique"][: uniq.shape[0]], s["host"]["lang_slot"][: hi - lo])
             with torch.cuda.stream(copy):
                 if i >= 2:
                     copy.wait_event(s["free"])            # kernels of chunk i-2 have consumed this slot
@@ -325,8 +331,6 @@ class MatchScorer:
             if group is not None:
                 dev_feeds["lang_unique"] = s["dev"]["lang_unique"][: group[0].shape[0]]
                 dev_feeds["lang_slot"] = s["dev"]["lang_slot"][: hi - lo]
-                s.setdefault("keep", []).append(group)    # pinned sources stay alive until the copy has run
-                del s["keep"][:-2]
             self.forward_device(dev_feeds, probs_out=s["probs"][: hi - lo])
             dev_probs[lo:hi].copy_(s["probs"][: hi - lo], non_blocking=True)
             s["free"].record(compute)
