@@ -15,11 +15,14 @@ _BOUND: Dict[str, dict] = {}
 MAX_BATCH = 256
 
 
-def bind(kind: str, weights: Dict[str, np.ndarray], device: int = 0, dtype: str = "fp16", **layers) -> None:
+def bind(kind: str, weights: Dict[str, np.ndarray], device: int = 0, dtype: str = "fp16", precision: str = "fast",
+         **layers) -> None:
     """Registers the checkpoint of one model kind (names as in the reference checkpoints).
-    `layers` overrides the depth (n_layers / n_r_layers / n_x_layers), e.g. for the 2-layer plumbing config."""
+    `layers` overrides the depth (n_layers / n_r_layers / n_x_layers), e.g. for the 2-layer plumbing config;
+    precision="strict" selects the two-term split-operand arithmetic (scorer.MatchScorer)."""
     release(kind)
-    _BOUND[kind] = {"weights": weights, "device": device, "dtype": dtype, "layers": layers, "scorers": {}}
+    _BOUND[kind] = {"weights": weights, "device": device, "dtype": dtype, "precision": precision, "layers": layers,
+                    "scorers": {}}
 
 
 def release(kind: Optional[str] = None) -> None:
@@ -66,7 +69,7 @@ def scorer_for(kind: str, lq: int, nbox: int, batch: int) -> MatchScorer:
     vocab = w["bert/embeddings/word_embeddings" if kind != LXMERT else
               "lxrt_encoder.model.bert.embeddings.word_embeddings.weight"].shape[0]
     cfg = ModelConfig(kind, lq=lq, nbox=nbox, vocab=int(vocab), **_depth(kind, w, b["layers"]))
-    sc = MatchScorer(cfg, w, device=b["device"], dtype=b["dtype"], max_batch=mb)
+    sc = MatchScorer(cfg, w, device=b["device"], dtype=b["dtype"], max_batch=mb, precision=b.get("precision", "fast"))
     b["scorers"][(lq, nbox, mb)] = sc
     return sc
 
