@@ -12,7 +12,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from kddcup_2020_multimodalitiesrecall_2nd_place_b200 import ensemble
-from kddcup_2020_multimodalitiesrecall_2nd_place_b200.scorer import allgather_scores, shard_range, sharded_score
+from kddcup_2020_multimodalitiesrecall_2nd_place_b200.scorer import (allgather_scores, distinct_queries, shard_range,
+                                                                      sharded_score, sharded_score_stream)
 
 
 class _StandInScorer:
@@ -24,6 +25,11 @@ class _StandInScorer:
         # integer arithmetic: bit-identical whatever the chunking (as the real kernels are, test_baseline_size_properties)
         s = ((feeds["query_ids"].long().sum(1) * 31 + (feeds["feats"] > 0).long().sum(dim=(1, 2)) * 7) % 1000).float() / 1000.0
         return torch.stack([1.0 - s, s], 1)
+
+    def score_stream(self, n, fetch):
+        """MatchScorer.score_stream's contract: fetch(lo, hi) in LOCAL indices, chunks of at most max_batch."""
+        out = [self.score(fetch(lo, min(n, lo + 5))) for lo in range(0, n, 5)]
+        return torch.cat(out) if out else torch.empty((0, 2))
 
 
 def _free_port():
@@ -49,6 +55,16 @@ def _worker(rank, world, port, n, out_dir):
         want = _StandInScorer().score(feeds)[:, 1]
         assert full.shape == (n,), full.shape
         assert torch.equal(full, want), (rank, (full - want).abs().max())
+        # the streamed variant: every rank fetches only pairs of its own range, in global indices
+        seen = []
+
+        def fetch(lo, hi):
+            seen.append((lo, hi))
+            return {k: v[lo:hi] for k, v in feeds.items()}
+        streamed = sharded_score_stream(_StandInScorer(), n, fetch, rank, world)
+        assert torch.equal(streamed, want)
+        lo, hi, _ = shard_range(n, rank, world)
+        assert all(lo <= a and b <= hi for a, b in seen) and sum(b - a for a, b in seen) == hi - lo
         # ragged: rank r contributes r+1 real scores, padded to 3
         mine = torch.full((3,), -1.0)
         mine[: rank + 1] = float(rank + 1)
@@ -83,3 +99,20 @@ def test_shard_range_covers_every_pair_once():
                 assert 0 <= lo <= hi <= n and hi - lo <= per
                 seen += list(range(lo, hi))
             assert seen == list(range(n))
+
+
+def test_distinct_queries_groups_pairs_by_query_and_mask():
+    """The host side of mmr_inputs.lang_unique / lang_slot: representatives ascending, every pair mapped to the first
+    pair with the same (ids, mask) row; two queries with equal ids but different masks stay apart."""
+    q = np.array([[5, 6, 0], [1, 2, 0], [5, 6, 0], [1, 2, 0], [9, 9, 9], [5, 6, 0]])
+    m = np.array([[1, 1, 0], [1, 1, 0], [1, 1, 0], [1, 1, 1], [1, 1, 1], [1, 1, 0]])
+    uniq, slot = distinct_queries(q, m)
+    assert uniq.dtype == torch.int32 and slot.dtype == torch.int32
+    assert uniq.tolist() == [0, 1, 3, 4] and slot.tolist() == [0, 1, 0, 2, 3, 0]
+    rng = np.random.default_rng(0)
+    pool = rng.integers(0, 50, (7, 12))
+    owner = rng.integers(0, 7, 200)
+    uniq, slot = distinct_queries(pool[owner], np.ones((200, 12), np.int64))
+    u, s_ = uniq.numpy(), slot.numpy()
+    assert (np.diff(u) > 0).all() and (pool[owner][u[s_]] == pool[owner]).all() and (u[s_] <= np.arange(200)).all()
+    assert len(u) == len(np.unique(owner))
