@@ -119,6 +119,172 @@ mmr_status cls_attention(const void* q, int64_t q_pair_stride, const void* k, co
   return MMR_OK;
 }
 
+// -------------------------------------------------------------------------------------------------------------------
+// The end of the last block in ONE kernel: LayerNorm of the FFN output (+ residual, already summed by the GEMM before),
+// pooler tanh(W . x[CLS] + b) (pixelbert.py:258-266, pixelmodel.py:251-259) and the 2-way match head -- AM-softmax
+// (model_triple.py:56-86) or linear + softmax (run_pretraining_predict_score.py:479-501) -- for the B [CLS] rows.
+// A cluster of four CTAs owns eight rows: every CTA normalises the eight rows into shared memory (24 KB, redundantly:
+// 6 K floats), computes ITS 192 pooler columns for them on the CUDA cores (one thread = one output column, its weight
+// row streamed from L2, the inputs broadcast from shared memory; 151 MFLOP in all -- a tensor-core launch for 256 rows
+// is latency, not throughput), reduces the head's three sums over its columns and sends them to the cluster's first
+// CTA through distributed shared memory, which finishes the softmax.  Replaces three launches (LayerNorm, pooler GEMM,
+// head: 6 + 18 + 5 us under ncu) of the [CLS] tail.
+constexpr int kPhRows = 8;          // rows per cluster
+constexpr int kPhCtas = 4;          // CTAs per cluster
+constexpr int kPhCols = 768 / kPhCtas;   // 192 pooler columns per CTA
+constexpr int kPhThreads = 256;
+
+template <class E16>
+__global__ void __cluster_dims__(kPhCtas, 1, 1) __launch_bounds__(kPhThreads)
+cls_pool_head_kernel(const float* __restrict__ y32, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     const typename E16::T* __restrict__ Wp, const float* __restrict__ bp, int head_kind,
+                     const float* __restrict__ hw, const float* __restrict__ hb, const int32_t* __restrict__ labels,
+                     int B, float* __restrict__ pooled32, float* __restrict__ probs, float* __restrict__ logits) {
+  __shared__ __align__(16) float xs[kPhRows][768];
+  __shared__ float part[kPhThreads / 32][kPhRows][3];
+  __shared__ float gather[kPhCtas][kPhRows][3];       // meaningful in the cluster's CTA 0
+  pdl_wait();
+  pdl_launch_dependents();
+  const uint32_t rank = cluster_ctarank();
+  const int row0 = int(blockIdx.x / kPhCtas) * kPhRows;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // ---- LayerNorm of row row0 + warp (biased variance, eps 1e-12), rounded to the operand type like the x16 mirror the
+  // tensor-core pooler reads
+  {
+    const int r = row0 + warp;
+    float4 v[6];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      v[i] = r < B ? *reinterpret_cast<const float4*>(y32 + int64_t(r) * 768 + (i * 32 + lane) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) * (1.0f / 768.0f);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / 768.0f) + 1e-12f);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const int c0 = (i * 32 + lane) * 4;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c0));
+      const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c0));
+      const float2 lo = E16::unpack(E16::pack((v[i].x - mean) * rstd * g.x + be.x, (v[i].y - mean) * rstd * g.y + be.y));
+      const float2 hi = E16::unpack(E16::pack((v[i].z - mean) * rstd * g.z + be.z, (v[i].w - mean) * rstd * g.w + be.w));
+      *reinterpret_cast<float4*>(&xs[warp][c0]) = make_float4(lo.x, lo.y, hi.x, hi.y);
+    }
+  }
+  __syncthreads();
+  // ---- pooler: thread t < 192 owns output column j; 8 rows at once
+  float sums[kPhRows][3];
+#pragma unroll
+  for (int r = 0; r < kPhRows; ++r) sums[r][0] = sums[r][1] = sums[r][2] = 0.f;
+  if (threadIdx.x < kPhCols) {
+    const int j = int(rank) * kPhCols + threadIdx.x;
+    const uint4* wrow = reinterpret_cast<const uint4*>(Wp + int64_t(j) * 768);
+    float acc[kPhRows];
+#pragma unroll
+    for (int r = 0; r < kPhRows; ++r) acc[r] = 0.f;
+#pragma unroll 2
+    for (int k8 = 0; k8 < 96; ++k8) {
+      const uint4 w = __ldg(wrow + k8);
+      const float2 w0 = E16::unpack(w.x), w1 = E16::unpack(w.y), w2 = E16::unpack(w.z), w3 = E16::unpack(w.w);
+#pragma unroll
+      for (int r = 0; r < kPhRows; ++r) {
+        const float4 a = *reinterpret_cast<const float4*>(&xs[r][k8 * 8]);
+        const float4 b = *reinterpret_cast<const float4*>(&xs[r][k8 * 8 + 4]);
+        float t = acc[r];
+        t = fmaf(a.x, w0.x, t); t = fmaf(a.y, w0.y, t); t = fmaf(a.z, w1.x, t); t = fmaf(a.w, w1.y, t);
+        t = fmaf(b.x, w2.x, t); t = fmaf(b.y, w2.y, t); t = fmaf(b.z, w3.x, t); t = fmaf(b.w, w3.y, t);
+        acc[r] = t;
+      }
+    }
+    const float bj = __ldg(bp + j);
+    const float h0 = __ldg(hw + j), h1 = __ldg(hw + 768 + j);       // head weights [2, 768]
+#pragma unroll
+    for (int r = 0; r < kPhRows; ++r) {
+      const float p = tanhf(acc[r] + bj);
+      if (row0 + r < B) pooled32[int64_t(row0 + r) * 768 + j] = p;
+      sums[r][0] = p * p;
+      sums[r][1] = p * h0;
+      sums[r][2] = p * h1;
+    }
+  }
+  // ---- head sums over this CTA's columns -> cluster CTA 0
+#pragma unroll
+  for (int r = 0; r < kPhRows; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float t = warp_sum(sums[r][c]);
+      if (lane == 0) part[warp][r][c] = t;
+    }
+  __syncthreads();
+  if (threadIdx.x < kPhRows * 3) {
+    const int r = threadIdx.x / 3, c = threadIdx.x % 3;
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kPhThreads / 32; ++w) t += part[w][r][c];
+    const uint32_t dst = mapa_u32(smem_u32(&gather[rank][r][c]), 0);
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(dst), "f"(t) : "memory");
+  }
+  cluster_sync_all();    // release / acquire at cluster scope: CTA 0 sees the four CTAs' partial sums
+  if (rank == 0 && threadIdx.x < kPhRows && row0 + int(threadIdx.x) < B) {
+    const int r = threadIdx.x, b = row0 + r;
+    float ss = 0.f, d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int q = 0; q < kPhCtas; ++q) {     // fixed order: the bits do not depend on which CTA arrives first
+      ss += gather[q][r][0];
+      d0 += gather[q][r][1];
+      d1 += gather[q][r][2];
+    }
+    float l0, l1;
+    if (head_kind == 0) {
+      // AM-softmax (model_triple.py:56-86): hw = column-normalised am_kernel, cosines, margin on the fed label, x 30
+      const float inv = rsqrtf(fmaxf(ss, 1e-12f));
+      float c0 = fminf(fmaxf(d0 * inv, -1.f), 1.f), c1 = fminf(fmaxf(d1 * inv, -1.f), 1.f);
+      const int y = labels[b];
+      const float g = y ? c1 : c0;
+      const float m = g > 0.35f ? 0.35f : 0.f;
+      if (y) c1 -= m; else c0 -= m;
+      l0 = 30.f * c0;
+      l1 = 30.f * c1;
+    } else {
+      l0 = d0 + hb[0];                       // run_pretraining_predict_score.py:491-492
+      l1 = d1 + hb[1];
+    }
+    const float mx = fmaxf(l0, l1);
+    const float e0 = expf(l0 - mx), e1 = expf(l1 - mx);
+    const float inv = 1.0f / (e0 + e1);
+    probs[2 * b] = e0 * inv;
+    probs[2 * b + 1] = e1 * inv;
+    if (logits != nullptr) {
+      logits[2 * b] = l0;
+      logits[2 * b + 1] = l1;
+    }
+  }
+}
+
+// head_kind 0: AM-softmax (hw = wn [2,768], labels); 1: linear (hw = W [2,768], hb [2]).
+mmr_status cls_pool_head(const float* y32, const float* gamma, const float* beta, const void* Wp16, const float* bp,
+                         int head_kind, const float* hw, const float* hb, const int32_t* labels, int B, float* pooled32,
+                         float* probs, float* logits, int dtype, cudaStream_t stream) {
+  MMR_TRY(require_sm100());
+  MMR_REQUIRE(y32 && gamma && beta && Wp16 && bp && hw && pooled32 && probs && B > 0, "cls_pool_head: null argument");
+  MMR_REQUIRE(head_kind == 0 ? labels != nullptr : hb != nullptr, "cls_pool_head: head parameters missing");
+  const int clusters = (B + kPhRows - 1) / kPhRows;
+  if (dtype == MMR_DT_BF16)
+    (void)launch_pdl(cls_pool_head_kernel<BF16>, dim3(clusters * kPhCtas), dim3(kPhThreads), 0, stream, y32, gamma, beta,
+                     static_cast<const BF16::T*>(Wp16), bp, head_kind, hw, hb, labels, B, pooled32, probs, logits);
+  else
+    (void)launch_pdl(cls_pool_head_kernel<FP16>, dim3(clusters * kPhCtas), dim3(kPhThreads), 0, stream, y32, gamma, beta,
+                     static_cast<const FP16::T*>(Wp16), bp, head_kind, hw, hb, labels, B, pooled32, probs, logits);
+  MMR_CUDA_OK(cudaGetLastError());
+  return MMR_OK;
+}
+
 }  // namespace mmr
 
 extern "C" mmr_status mmr_cls_attention(const void* q, int64_t q_pair_stride, const void* k, const void* v, int64_t ldkv,

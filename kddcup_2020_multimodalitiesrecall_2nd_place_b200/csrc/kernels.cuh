@@ -94,6 +94,10 @@ mmr_status lx_box_ln(const float* boxes4, const float* Wb, const float* bb, cons
 mmr_status cls_attention(const void* q, int64_t q_pair_stride, const void* k, const void* v, int64_t ldkv,
                          const int32_t* key_mask, void* out16, int64_t ldo, int B, int Sk, int heads, int dtype,
                          cudaStream_t stream);
+// LayerNorm + pooler + 2-way head of the B [CLS] rows in one kernel (cls_tail.cu); head_kind 0 AM-softmax, 1 linear
+mmr_status cls_pool_head(const float* y32, const float* gamma, const float* beta, const void* Wp16, const float* bp,
+                         int head_kind, const float* hw, const float* hb, const int32_t* labels, int B, float* pooled32,
+                         float* probs, float* logits, int dtype, cudaStream_t stream);
 // strict precision mode (strict.cu): two-term operand split, precise activations, fp32 attention
 mmr_status split3(const float* x, int64_t ldx, int rows, int K, void* out16, int64_t ldo, int act, int weights, int dtype,
                   cudaStream_t stream);

@@ -783,7 +783,7 @@ static mmr_status pooler(Ctx& c, int B, int S, bool compact) {
 // their block INPUT, the B first rows leave through the compact xc16 / xc32 buffers.  Keys and values are projected
 // for every row (they feed the [CLS] query), everything after the attention runs on B rows.
 static mmr_status cls_tail_block(Ctx& c, const AttBlock& A, const FfnBlock& F, int64_t row0, int B, int S,
-                                 const int32_t* key_mask) {
+                                 const int32_t* key_mask, bool final_ln = true) {
   mmr_handle* h = c.h;
   const int H = c.H;
   MMR_TRY(qkv_proj(c, A.qkv, row0, B * S));
@@ -801,6 +801,7 @@ static mmr_status cls_tail_block(Ctx& c, const AttBlock& A, const FfnBlock& F, i
   MMR_TRY(c.LN(h->xc32, A.ln, B, h->xc16, h->xc32, 1.0f, 0));
   MMR_TRY(tail_gemm(h->xc16, H, F.in, nullptr, 0, h->hc16, F.in.n, nullptr, h->act));
   MMR_TRY(tail_gemm(h->hc16, F.in.n, F.out, h->xc32, H, nullptr, 0, h->xc32, MMR_ACT_NONE));
+  if (!final_ln) return MMR_OK;   // the block's last LayerNorm is fused into the pooler + head kernel that follows
   return c.LN(h->xc32, F.ln, B, h->xc16, h->xc32, 1.0f, 0);
 }
 
@@ -860,15 +861,19 @@ static mmr_status forward_single_stream(Ctx& c, const mmr_inputs* in, int B, flo
   const bool prune = prune_last(h);
   for (size_t i = 0; i < h->layers.size(); ++i) {
     if (prune && i + 1 == h->layers.size()) {
-      MMR_TRY(cls_tail_block(c, h->layers[i].att, h->layers[i].ffn, 0, B, S, mask));
-      break;
+      // [CLS] rows only, and the block's last LayerNorm + pooler + match head as ONE kernel (cls_tail.cu)
+      MMR_TRY(cls_tail_block(c, h->layers[i].att, h->layers[i].ffn, 0, B, S, mask, false));
+      const LNp& ln = h->layers[i].ffn.ln;
+      MMR_TRY(cls_pool_head(h->xc32, ln.gamma, ln.beta, h->pooler.w16, h->pooler.bias, zk ? 0 : 1, zk ? h->am_wn : h->cls_w,
+                            zk ? nullptr : h->cls_b, zk ? in->labels : nullptr, B, h->pooled32, probs, logits, c.dt, c.st));
+      return c.mark(K_ROW, 2.0 * B * H * H);
     }
     MMR_TRY(bert_layer(c, h->layers[i], 0, B, S, mask));
     if (h->layer_tap != nullptr && h->keep_taps >= 2)
       MMR_CUDA_OK(cudaMemcpyAsync(h->layer_tap + i * size_t(h->rows_max) * H, h->x32, size_t(B) * S * H * 4,
                                   cudaMemcpyDeviceToDevice, c.st));
   }
-  MMR_TRY(pooler(c, B, S, prune));
+  MMR_TRY(pooler(c, B, S, false));
   if (zk)
     MMR_TRY(zk_head(h->pooled32, h->am_wn, in->labels, B, probs, logits, c.st));
   else
