@@ -124,15 +124,18 @@ mmr_status cls_attention(const void* q, int64_t q_pair_stride, const void* k, co
 // pooler tanh(W . x[CLS] + b) (pixelbert.py:258-266, pixelmodel.py:251-259) and the 2-way match head -- AM-softmax
 // (model_triple.py:56-86) or linear + softmax (run_pretraining_predict_score.py:479-501) -- for the B [CLS] rows.
 // A cluster of four CTAs owns eight rows: every CTA normalises the eight rows into shared memory (24 KB, redundantly:
-// 6 K floats), computes ITS 192 pooler columns for them on the CUDA cores (one thread = one output column, its weight
-// row streamed from L2, the inputs broadcast from shared memory; 151 MFLOP in all -- a tensor-core launch for 256 rows
-// is latency, not throughput), reduces the head's three sums over its columns and sends them to the cluster's first
+// 6 K floats), computes ITS 192 pooler columns for them on the CUDA cores (four adjacent lanes = four output columns,
+// each lane taking every fourth 8-element chunk of their weight rows streamed from L2; the inputs are broadcast from
+// shared memory, and 8 rows x 4 columns per thread is what keeps that broadcast -- 4 passes per LDS.128 whatever the
+// lanes read -- off the critical path: one thread = one column measured 30 us, bound by exactly that; 151 MFLOP in all,
+// a tensor-core launch for 256 rows is latency, not throughput), reduces the head's three sums
+// over its columns and sends them to the cluster's first
 // CTA through distributed shared memory, which finishes the softmax.  Replaces three launches (LayerNorm, pooler GEMM,
 // head: 6 + 18 + 5 us under ncu) of the [CLS] tail.
 constexpr int kPhRows = 8;          // rows per cluster
 constexpr int kPhCtas = 4;          // CTAs per cluster
 constexpr int kPhCols = 768 / kPhCtas;   // 192 pooler columns per CTA
-constexpr int kPhThreads = 256;
+constexpr int kPhThreads = 256;      // 8 LayerNorm warps; 192 of the threads = 48 column quads x 4 interleaved K quarters
 
 template <class E16>
 __global__ void __cluster_dims__(kPhCtas, 1, 1) __launch_bounds__(kPhThreads)
@@ -150,7 +153,7 @@ cls_pool_head_kernel(const float* __restrict__ y32, const float* __restrict__ ga
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // ---- LayerNorm of row row0 + warp (biased variance, eps 1e-12), rounded to the operand type like the x16 mirror the
   // tensor-core pooler reads
-  {
+  if (warp < kPhRows) {
     const int r = row0 + warp;
     float4 v[6];
     float s = 0.f;
@@ -178,35 +181,69 @@ cls_pool_head_kernel(const float* __restrict__ y32, const float* __restrict__ ga
     }
   }
   __syncthreads();
-  // ---- pooler: thread t < 192 owns output column j; 8 rows at once
+  // ---- pooler: lanes 4g .. 4g + 3 own the output columns 4g .. 4g + 3 of this CTA; lane quarter q takes the
+  // 8-element chunks k8 = 4 i + q of the four weight rows (the four lanes read 64 contiguous bytes of a row; their
+  // shared-memory reads hit four different bank groups), 8 rows x 4 columns of accumulators per thread, the weight
+  // chunks of the next iteration in flight while this one is multiplied
   float sums[kPhRows][3];
 #pragma unroll
   for (int r = 0; r < kPhRows; ++r) sums[r][0] = sums[r][1] = sums[r][2] = 0.f;
   if (threadIdx.x < kPhCols) {
-    const int j = int(rank) * kPhCols + threadIdx.x;
-    const uint4* wrow = reinterpret_cast<const uint4*>(Wp + int64_t(j) * 768);
-    float acc[kPhRows];
+    const int q = threadIdx.x & 3;
+    const int j0 = int(rank) * kPhCols + (threadIdx.x >> 2) * 4;
+    const uint4* wrow = reinterpret_cast<const uint4*>(Wp + int64_t(j0) * 768);   // rows j0 .. j0 + 3, 96 uint4 apart
+    float acc[kPhRows][4];
 #pragma unroll
-    for (int r = 0; r < kPhRows; ++r) acc[r] = 0.f;
-#pragma unroll 2
-    for (int k8 = 0; k8 < 96; ++k8) {
-      const uint4 w = __ldg(wrow + k8);
-      const float2 w0 = E16::unpack(w.x), w1 = E16::unpack(w.y), w2 = E16::unpack(w.z), w3 = E16::unpack(w.w);
+    for (int r = 0; r < kPhRows; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+    uint4 wn[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) wn[c] = __ldg(wrow + c * 96 + q);
+#pragma unroll 1
+    for (int i = 0; i < 24; ++i) {
+      uint4 w[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) w[c] = wn[c];
+      if (i + 1 < 24) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) wn[c] = __ldg(wrow + c * 96 + 4 * (i + 1) + q);
+      }
+      const int k = (4 * i + q) * 8;
+      float2 wf[4][4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        wf[c][0] = E16::unpack(w[c].x); wf[c][1] = E16::unpack(w[c].y);
+        wf[c][2] = E16::unpack(w[c].z); wf[c][3] = E16::unpack(w[c].w);
+      }
 #pragma unroll
       for (int r = 0; r < kPhRows; ++r) {
-        const float4 a = *reinterpret_cast<const float4*>(&xs[r][k8 * 8]);
-        const float4 b = *reinterpret_cast<const float4*>(&xs[r][k8 * 8 + 4]);
-        float t = acc[r];
-        t = fmaf(a.x, w0.x, t); t = fmaf(a.y, w0.y, t); t = fmaf(a.z, w1.x, t); t = fmaf(a.w, w1.y, t);
-        t = fmaf(b.x, w2.x, t); t = fmaf(b.y, w2.y, t); t = fmaf(b.z, w3.x, t); t = fmaf(b.w, w3.y, t);
-        acc[r] = t;
+        const float4 a = *reinterpret_cast<const float4*>(&xs[r][k]);
+        const float4 b = *reinterpret_cast<const float4*>(&xs[r][k + 4]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float t = acc[r][c];
+          t = fmaf(a.x, wf[c][0].x, t); t = fmaf(a.y, wf[c][0].y, t); t = fmaf(a.z, wf[c][1].x, t); t = fmaf(a.w, wf[c][1].y, t);
+          t = fmaf(b.x, wf[c][2].x, t); t = fmaf(b.y, wf[c][2].y, t); t = fmaf(b.z, wf[c][3].x, t); t = fmaf(b.w, wf[c][3].y, t);
+          acc[r][c] = t;
+        }
       }
     }
+#pragma unroll
+    for (int r = 0; r < kPhRows; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {            // the four K quarters of a column, in a fixed order
+        acc[r][c] += __shfl_xor_sync(0xffffffffu, acc[r][c], 1);
+        acc[r][c] += __shfl_xor_sync(0xffffffffu, acc[r][c], 2);
+      }
+    // lane quarter q finishes column j0 + q
+    const int j = j0 + q;
     const float bj = __ldg(bp + j);
     const float h0 = __ldg(hw + j), h1 = __ldg(hw + 768 + j);       // head weights [2, 768]
 #pragma unroll
     for (int r = 0; r < kPhRows; ++r) {
-      const float p = tanhf(acc[r] + bj);
+      const float pre = q == 0 ? acc[r][0] : (q == 1 ? acc[r][1] : (q == 2 ? acc[r][2] : acc[r][3]));
+      const float p = tanhf(pre + bj);
       if (row0 + r < B) pooled32[int64_t(row0 + r) * 768 + j] = p;
       sums[r][0] = p * p;
       sums[r][1] = p * h0;
