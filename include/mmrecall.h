@@ -314,6 +314,10 @@ typedef struct {
 
 mmr_status mmr_create(const mmr_config* cfg, const mmr_tensor* weights, int n_weights, int device,
                       mmr_handle** out);
+/* Device memory mmr_create will allocate for `cfg`: the packed-weight arena (16-bit matrices, fp32 tables; zk adds the
+ * 8 x vocab x 768 label-conv tables) and the per-forward workspace sized for max_batch.  No GPU needed; either output
+ * may be NULL.  (sizing query of the boundary.) */
+mmr_status mmr_workspace_bytes(const mmr_config* cfg, size_t* weight_bytes, size_t* workspace_bytes);
 void mmr_destroy(mmr_handle* h);
 
 /* Concurrency: a handle is not re-entrant, and the fused GEMM+LayerNorm kernel needs its whole grid co-resident, so

@@ -529,7 +529,7 @@ done:
   return rc;
 }
 
-static mmr_status alloc_workspace(mmr_handle* h) {
+static mmr_status alloc_workspace(mmr_handle* h, size_t* size_only = nullptr) {
   const mmr_config& c = h->cfg;
   const int64_t H = c.hidden, I = c.intermediate, B = c.max_batch, R = c.nbox;
   int64_t S = c.lq + c.nbox;
@@ -594,6 +594,10 @@ static mmr_status alloc_workspace(mmr_handle* h) {
     }
     if (pass == 0) {
       bytes += 4096;
+      if (size_only != nullptr) {      // mmr_workspace_bytes: the plan without the allocation
+        *size_only = bytes;
+        return MMR_OK;
+      }
       MMR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->work.base), bytes));
       h->work.cap = bytes;
       continue;
@@ -1227,6 +1231,22 @@ extern "C" mmr_status mmr_create(const mmr_config* cfg, const mmr_tensor* weight
     return rc;
   }
   *out = h;
+  return MMR_OK;
+}
+
+extern "C" mmr_status mmr_workspace_bytes(const mmr_config* cfg, size_t* weight_bytes, size_t* workspace_bytes) {
+  using namespace mmr;
+  MMR_REQUIRE(cfg && (weight_bytes || workspace_bytes), "mmr_workspace_bytes: null argument");
+  MMR_REQUIRE(cfg->model_kind >= 0 && cfg->model_kind <= 2 && cfg->lq > 0 && cfg->nbox > 0 && cfg->max_batch > 0 &&
+                  cfg->hidden > 0 && cfg->intermediate > 0 && cfg->feat_dim > 0,
+              "mmr_workspace_bytes: bad configuration");
+  if (weight_bytes) *weight_bytes = weight_arena_bytes(*cfg);
+  if (workspace_bytes) {
+    mmr_handle plan;
+    plan.cfg = *cfg;
+    plan.strict = cfg->precision == MMR_PRECISION_STRICT;
+    MMR_TRY(alloc_workspace(&plan, workspace_bytes));
+  }
   return MMR_OK;
 }
 

@@ -58,3 +58,24 @@ def test_product_never_imports_the_oracle():
             if f.endswith(".py"):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+
+
+def test_workspace_bytes_is_a_host_side_plan():
+    """mmr_workspace_bytes needs no GPU: cfg2 (12-layer zk, 32 x 36, batch 256) plans ~0.75 GB of weights (0.52 GB of it
+    the label-conv tables) and ~0.6 GB of workspace; strict precision triples the matrices and swaps the activations."""
+    lib = _lib.load(build_if_missing=True)
+
+    def plan(kind, precision, batch=256, n_layers=12, r=0, x=0):
+        c = _lib.MmrConfig(model_kind=kind, dtype=0, hidden=768, heads=12, intermediate=3072, vocab=21128, max_pos=512,
+                           type_vocab=2, feat_dim=2048, label_len=8, n_layers=n_layers, n_r_layers=r, n_x_layers=x, lq=32,
+                           nbox=36, max_batch=batch, precision=precision)
+        w, ws = ctypes.c_size_t(), ctypes.c_size_t()
+        _lib.check(lib.mmr_workspace_bytes(ctypes.byref(c), ctypes.byref(w), ctypes.byref(ws)))
+        return w.value, ws.value
+    w, ws = plan(_lib.MODEL_ZK, 0)
+    assert 0.7e9 < w < 0.9e9 and 0.4e9 < ws < 0.9e9
+    w2, ws2 = plan(_lib.MODEL_ZK, 1)
+    assert w2 > w + 0.3e9 and ws2 > ws
+    assert plan(_lib.MODEL_ZK, 0, batch=128)[1] < ws
+    wl, _ = plan(_lib.MODEL_LXMERT, 0, n_layers=9, r=5, x=5)
+    assert 0.3e9 < wl < 0.6e9
