@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <algorithm>
 #include <string>
 #include <vector>
@@ -218,6 +219,7 @@ struct DeviceTail {
   const mmr_handle* owner = nullptr;
 };
 static DeviceTail g_tail[64];
+static std::mutex g_tail_mu;   // host threads driving different handles of one device
 
 __global__ void transpose32_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
   // dst [cols, rows] = src [rows, cols]^T
@@ -1254,7 +1256,10 @@ extern "C" void mmr_destroy(mmr_handle* h) {
   if (!h) return;
   mmr::DeviceGuard guard(h->device);
   cudaDeviceSynchronize();   // nothing of this handle may still run when its arenas (and exchange table) go away
-  if (h->device >= 0 && h->device < 64 && mmr::g_tail[h->device].owner == h) mmr::g_tail[h->device] = mmr::DeviceTail();
+  {
+    std::lock_guard<std::mutex> lock(mmr::g_tail_mu);
+    if (h->device >= 0 && h->device < 64 && mmr::g_tail[h->device].owner == h) mmr::g_tail[h->device] = mmr::DeviceTail();
+  }
   if (h->done_ev) cudaEventDestroy(h->done_ev);
   if (h->weights.base) cudaFree(h->weights.base);
   if (h->work.base) cudaFree(h->work.base);
@@ -1276,7 +1281,10 @@ extern "C" mmr_status mmr_forward(mmr_handle* h, const mmr_inputs* in, int B, fl
   MMR_CUDA_OK(cudaStreamIsCapturing(c.st, &cap));
   const bool eager = cap == cudaStreamCaptureStatusNone;
   DeviceTail& tail = g_tail[h->device];
-  if (eager && tail.ev != nullptr && tail.stream != c.st) MMR_CUDA_OK(cudaStreamWaitEvent(c.st, tail.ev, 0));
+  if (eager) {
+    std::lock_guard<std::mutex> lock(g_tail_mu);
+    if (tail.ev != nullptr && tail.stream != c.st) MMR_CUDA_OK(cudaStreamWaitEvent(c.st, tail.ev, 0));
+  }
   if (h->prof_on) {
     h->prof_n = 0;
     MMR_CUDA_OK(cudaEventRecord(h->prof_ev[0], c.st));
@@ -1293,6 +1301,7 @@ extern "C" mmr_status mmr_forward(mmr_handle* h, const mmr_inputs* in, int B, fl
     MMR_CUDA_OK(cudaMemcpyAsync(pooled_out, h->pooled32, size_t(B) * h->cfg.hidden * 4, cudaMemcpyDeviceToDevice,
                                 c.st));
   if (eager) {
+    std::lock_guard<std::mutex> lock(g_tail_mu);
     MMR_CUDA_OK(cudaEventRecord(h->done_ev, c.st));
     tail.ev = h->done_ev;
     tail.stream = c.st;
