@@ -20,17 +20,27 @@
 namespace mmr {
 
 constexpr int kBM = 128;       // rows per tile (= UMMA M, one TMEM lane per row)
-constexpr int kStages = 4;
 constexpr int kThreads = kGemmThreads;
 constexpr uint32_t kABytes = kBM * kBK * 2;
-constexpr uint32_t kBBytes = kBN * kBK * 2;
-constexpr uint32_t kStageBytes = kABytes + kBBytes;
-constexpr size_t kSmemBytes = 1024 /*align slack*/ + size_t(kStages) * kStageBytes + 256 /*barriers*/ + kEpiSmemBytes;
+// Two shapes of the same kernel: 256-column tiles with a 4-stage operand ring (general), and 64-column tiles with an
+// 8-stage ring for the few-row launches of the last block's [CLS] tail (M = B <= 512): there a tile's K loop is a chain
+// of TMA latencies on a handful of CTAs, and narrow tiles put 4x the CTAs on it with twice the loads in flight.
+template <int BN_T, int STAGES>
+struct SingleCfg {
+  static constexpr int kBnT = BN_T, kStages = STAGES;
+  static constexpr uint32_t kBBytes = BN_T * kBK * 2;
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr size_t kSmemBytes = 1024 /*align slack*/ + size_t(STAGES) * kStageBytes + 256 /*barriers*/ + kEpiSmemBytes;
+};
+using SingleWide = SingleCfg<kBN, 4>;
+using SingleNarrow = SingleCfg<64, 8>;
 
-template <int ACT, class E16>
+template <int ACT, class E16, class CFG>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                     const GemmParams p) {
+  constexpr int kStages = CFG::kStages, kBnT = CFG::kBnT;
+  constexpr uint32_t kBBytes = CFG::kBBytes, kStageBytes = CFG::kStageBytes;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -48,7 +58,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int lane = threadIdx.x & 31;
 
   const int m_tiles = (p.M + kBM - 1) / kBM;
-  const int n_tiles = (p.N + kBN - 1) / kBN;
+  const int n_tiles = (p.N + kBnT - 1) / kBnT;
   const int k_blocks = p.K / kBK;
   const int total_tiles = m_tiles * n_tiles;
 
@@ -89,7 +99,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           mbar_arrive_expect_tx(&full_bar[stage], tx);
           tma_load_2d(smem_a + size_t(stage) * kABytes, &tmap_a, &full_bar[stage], kb * kBK, m_blk * kBM);
-          tma_load_2d(smem_b + size_t(stage) * kBBytes, &tmap_w, &full_bar[stage], kb * kBK, n_blk * kBN);
+          tma_load_2d(smem_b + size_t(stage) * kBBytes, &tmap_w, &full_bar[stage], kb * kBK, n_blk * kBnT);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -102,13 +112,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int n_blk = tile % n_tiles;
-        const int bn = min(kBN, p.N - n_blk * kBN);
+        const int bn = min(kBnT, p.N - n_blk * kBnT);
         const uint32_t idesc = umma_idesc_f16(p.idesc_fmt, kBM, uint32_t(bn));
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1u;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + uint32_t(acc) * kBN;
+        const uint32_t tmem_d = tmem_base + uint32_t(acc) * kBnT;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -136,14 +146,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-      const int bn = min(kBN, p.N - n_blk * kBN);
+      const int bn = min(kBnT, p.N - n_blk * kBnT);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const int row0 = m_blk * kBM + quarter * 32;
-      const uint32_t taddr_row = tmem_base + uint32_t(acc) * kBN + (uint32_t(quarter * 32) << 16);
-      epilogue_warp<ACT, E16>(p, taddr_row, row0, n_blk * kBN, bn, half, epi_stage + ew * kEpiStageFloats);
+      const uint32_t taddr_row = tmem_base + uint32_t(acc) * kBnT + (uint32_t(quarter * 32) << 16);
+      epilogue_warp<ACT, E16>(p, taddr_row, row0, n_blk * kBnT, bn, half, epi_stage + ew * kEpiStageFloats);
       // all of this warp's TMEM reads of accumulator `acc` are complete -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -234,28 +244,28 @@ int sm_count() {
   return n;
 }
 
-template <int ACT, class E16>
+template <int ACT, class E16, class CFG>
 static mmr_status launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, int grid,
                               cudaStream_t stream) {
-  auto kern = gemm_tcgen05_kernel<ACT, E16>;
+  auto kern = gemm_tcgen05_kernel<ACT, E16, CFG>;
   static bool configured = false;
   if (!configured) {
-    MMR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
+    MMR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(CFG::kSmemBytes)));
     configured = true;
   }
-  MMR_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(kThreads), kSmemBytes, stream, ta, tw, p));
+  MMR_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(kThreads), CFG::kSmemBytes, stream, ta, tw, p));
   return MMR_OK;
 }
 
-template <class E16>
+template <class E16, class CFG>
 static mmr_status dispatch_act(int act, const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p,
                                int grid, cudaStream_t s) {
   switch (act) {
-    case MMR_ACT_NONE: return launch_gemm<MMR_ACT_NONE, E16>(ta, tw, p, grid, s);
-    case MMR_ACT_RELU: return launch_gemm<MMR_ACT_RELU, E16>(ta, tw, p, grid, s);
-    case MMR_ACT_GELU_TANH: return launch_gemm<MMR_ACT_GELU_TANH, E16>(ta, tw, p, grid, s);
-    case MMR_ACT_GELU_ERF: return launch_gemm<MMR_ACT_GELU_ERF, E16>(ta, tw, p, grid, s);
-    case MMR_ACT_TANH: return launch_gemm<MMR_ACT_TANH, E16>(ta, tw, p, grid, s);
+    case MMR_ACT_NONE: return launch_gemm<MMR_ACT_NONE, E16, CFG>(ta, tw, p, grid, s);
+    case MMR_ACT_RELU: return launch_gemm<MMR_ACT_RELU, E16, CFG>(ta, tw, p, grid, s);
+    case MMR_ACT_GELU_TANH: return launch_gemm<MMR_ACT_GELU_TANH, E16, CFG>(ta, tw, p, grid, s);
+    case MMR_ACT_GELU_ERF: return launch_gemm<MMR_ACT_GELU_ERF, E16, CFG>(ta, tw, p, grid, s);
+    case MMR_ACT_TANH: return launch_gemm<MMR_ACT_TANH, E16, CFG>(ta, tw, p, grid, s);
     default: return fail(MMR_ERR_INVALID, "mmr_gemm: unknown activation %d", act);
   }
 }
@@ -290,14 +300,21 @@ mmr_status gemm(const void* A16, int64_t lda, const void* W16, int64_t ldw, int 
   }
   CUtensorMap ta, tw;
   MMR_TRY(make_tmap_2d(&ta, A16, M, K, lda, kBM, dtype));
-  // Box rows for W: a full 256-row box when N allows it, else exactly N rows (N < 256).
-  const int w_box = N >= kBN ? kBN : N;
+  // few rows (the [CLS] tail): 64-column tiles, 8-stage ring; else 256-column tiles
+  const bool narrow = single_cta_only && M <= 512 && N >= 64;
+  const int bn_t = narrow ? SingleNarrow::kBnT : kBN;
+  // Box rows for W: a full tile-wide box when N allows it, else exactly N rows.
+  const int w_box = N >= bn_t ? bn_t : N;
   MMR_TRY(make_tmap_2d(&tw, W16, N, K, ldw, w_box, dtype));
   GemmParams p{M, N, K, bias, residual, ldr, out16, ldo16, out32, ldo32, uint32_t(dtype), uint32_t(w_box)};
-  const int tiles = ((M + kBM - 1) / kBM) * ((N + kBN - 1) / kBN);
+  const int tiles = ((M + kBM - 1) / kBM) * ((N + bn_t - 1) / bn_t);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  if (dtype == MMR_DT_BF16) return dispatch_act<BF16>(act, ta, tw, p, grid, stream);
-  return dispatch_act<FP16>(act, ta, tw, p, grid, stream);
+  if (narrow) {
+    if (dtype == MMR_DT_BF16) return dispatch_act<BF16, SingleNarrow>(act, ta, tw, p, grid, stream);
+    return dispatch_act<FP16, SingleNarrow>(act, ta, tw, p, grid, stream);
+  }
+  if (dtype == MMR_DT_BF16) return dispatch_act<BF16, SingleWide>(act, ta, tw, p, grid, stream);
+  return dispatch_act<FP16, SingleWide>(act, ta, tw, p, grid, stream);
 }
 
 }  // namespace mmr
