@@ -286,16 +286,21 @@ class MatchScorer:
         N = feeds_host["query_ids"].shape[0]
         return self.score_stream(N, lambda lo, hi: {n: feeds_host[n][lo:hi] for n in self.spec}, out)
 
-    def score_stream(self, n_pairs: int, fetch, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def score_stream(self, n_pairs: int, fetch, out: Optional[torch.Tensor] = None, on_device: bool = False) -> torch.Tensor:
         """The same pipeline over a pair list that need not be resident as one array: `fetch(lo, hi)` returns the feeds
         of pairs [lo, hi) (hi - lo <= max_batch; a decoder's batch arrays, a window of a memory-mapped file, ...; host or
         device tensors).  `fetch` may reuse its buffers every SECOND call: before call k, the copies that read what call
-        k - 2 returned have completed."""
+        k - 2 returned have completed.  on_device=True returns the [N, 2] probabilities as a DEVICE tensor, asynchronously
+        on the current stream (no host copy, no synchronisation): what the sharded path gathers from."""
         N = int(n_pairs)
-        if out is None:
-            out = torch.empty((N, 2), dtype=torch.float32).pin_memory()
-        if N == 0:
-            return out
+        if on_device:
+            if N == 0:
+                return torch.empty((0, 2), dtype=torch.float32, device=self.device)
+        else:
+            if out is None:
+                out = torch.empty((N, 2), dtype=torch.float32).pin_memory()
+            if N == 0:
+                return out
         slots = self._make_slots()
         compute = torch.cuda.current_stream(self.device)
         copy = self._copy_stream
@@ -334,6 +339,8 @@ class MatchScorer:
             self.forward_device(dev_feeds, probs_out=s["probs"][: hi - lo])
             dev_probs[lo:hi].copy_(s["probs"][: hi - lo], non_blocking=True)
             s["free"].record(compute)
+        if on_device:
+            return dev_probs
         out.copy_(dev_probs, non_blocking=True)
         compute.synchronize()
         return out
@@ -346,27 +353,31 @@ def sharded_score(scorer: MatchScorer, feeds_host: Dict[str, torch.Tensor], rank
     (NCCL over NVLink when the process group is nccl; gloo in the CPU tests of the host logic).  Returns the full
     [N] score vector on every rank (CPU tensor)."""
     N = feeds_host["query_ids"].shape[0]
-    lo, hi, per = shard_range(N, rank, world)
-    local = {k: v[lo:hi] for k, v in feeds_host.items() if k in scorer.spec}
-    probs = scorer.score(local) if hi > lo else torch.empty((0, 2))
-    return _finish_shard(scorer, probs, N, lo, hi, per, world, gather)
+    return sharded_score_stream(scorer, N, lambda lo, hi: {k: feeds_host[k][lo:hi] for k in scorer.spec}, rank, world,
+                                gather)
 
 
 def sharded_score_stream(scorer: MatchScorer, n_pairs: int, fetch, rank: int, world: int,
                          gather: bool = True) -> torch.Tensor:
     """sharded_score over a pair list given by `fetch(lo, hi)` in GLOBAL pair indices: every rank touches only the
-    host feeds of its own range (at cfg4 a rank stages 1.1 GB instead of the whole 8.8 GB candidate set)."""
+    host feeds of its own range (at cfg4 a rank stages 1.1 GB instead of the whole 8.8 GB candidate set).  Under NCCL
+    the shard's scores go from the scorer's device buffer straight into the all-gather -- no host round trip."""
+    import torch.distributed as dist
     lo, hi, per = shard_range(n_pairs, rank, world)
-    probs = scorer.score_stream(hi - lo, lambda a, b: fetch(lo + a, lo + b)) if hi > lo else torch.empty((0, 2))
-    return _finish_shard(scorer, probs, n_pairs, lo, hi, per, world, gather)
-
-
-def _finish_shard(scorer, probs, N, lo, hi, per, world, gather):
+    local = lambda a, b: fetch(lo + a, lo + b)
+    if gather and world > 1 and dist.is_initialized() and dist.get_backend() == "nccl" and hasattr(scorer, "device"):
+        probs = scorer.score_stream(hi - lo, local, on_device=True)
+        mine = torch.zeros(per, dtype=torch.float32, device=scorer.device)
+        mine[: hi - lo] = probs[:, 1]
+        out = torch.empty(world * per, dtype=torch.float32, device=scorer.device)
+        dist.all_gather_into_tensor(out, mine)
+        return out[:n_pairs].cpu()
+    probs = scorer.score_stream(hi - lo, local) if hi > lo else torch.empty((0, 2))
     mine = torch.zeros(per, dtype=torch.float32)
     mine[: hi - lo] = probs[:, 1]
     if not gather or world == 1:
         return mine[: hi - lo] if world == 1 else mine
-    return allgather_scores(mine, N, world, scorer.device)
+    return allgather_scores(mine, n_pairs, world, scorer.device)
 
 
 def shard_range(n: int, rank: int, world: int):
