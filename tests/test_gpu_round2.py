@@ -584,3 +584,23 @@ def test_bf16_operands_in_strict_mode_meet_the_tolerance(kind):
     print(f"{kind} bf16 operands: max|dscore| fast = {errs['fast']:.3e}, strict = {errs['strict']:.3e}")
     assert errs["strict"] <= TOL
     assert errs["fast"] <= 3e-2
+
+
+@pytest.mark.parametrize("kind", [ZK, LDS, LXMERT])
+def test_odd_batch_sizes_through_the_cls_tail(kind):
+    """B = 1, 7 and 9 pairs (not multiples of the 8-row clusters of the fused pooler + head kernel, a single pair, a
+    max_batch larger than the batch) against the oracle, native 20 x 10 shapes, 2 layers."""
+    cfg = (ModelConfig(LXMERT, n_layers=2, n_r_layers=1, n_x_layers=2, lq=23, nbox=10, vocab=2000) if kind == LXMERT
+           else ModelConfig(kind, n_layers=2, lq=20, nbox=10, vocab=2000))
+    w = synth.make_weights(cfg, seed=synth.SEED0 + 81)
+    sc = _scorer(cfg, w, 16)
+    try:
+        for B in (1, 7, 9):
+            inp = synth.make_inputs(cfg, B, seed=synth.SEED0 + 81 + B, n_queries=max(1, B // 3))
+            ref = _oracle(cfg, w, inp)
+            probs, pooled = _gpu(sc, inp)
+            assert (probs - ref["probs"]).abs().max().item() <= TOL, (kind, B)
+            assert (pooled - ref["pooled"]).abs().max().item() <= 5e-3, (kind, B)
+            assert torch.allclose(probs.sum(1), torch.ones(B), atol=1e-6)
+    finally:
+        sc.close()
