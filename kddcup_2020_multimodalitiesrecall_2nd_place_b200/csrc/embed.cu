@@ -333,7 +333,7 @@ lds_embed_kernel(const int32_t* __restrict__ query_ids, const int32_t* __restric
 // lang0 = LN(E[q] + Pos[s] + Ttype[0])  (modeling.py:283-297)
 template <class E16>
 __global__ void __launch_bounds__(256)
-lx_lang_embed_kernel(const int32_t* __restrict__ query_ids, const int32_t* __restrict__ pair_map,
+lx_lang_embed_kernel(const int32_t* __restrict__ query_ids, const int32_t* __restrict__ pair_map, int n_map,
                      const float* __restrict__ E, const float* __restrict__ T, const float* __restrict__ P,
                      const float* __restrict__ gamma, const float* __restrict__ beta, int Lq, int rows,
                      typename E16::T* __restrict__ x16, float* __restrict__ x32) {
@@ -344,7 +344,8 @@ lx_lang_embed_kernel(const int32_t* __restrict__ query_ids, const int32_t* __res
   const int lane = threadIdx.x & 31;
   const int s = row % Lq;
   // output row group u embeds the query of pair pair_map[u] (one row group per DISTINCT query), or of pair u itself
-  const int src_pair = pair_map != nullptr ? __ldg(pair_map + row / Lq) : row / Lq;
+  // (row groups beyond the n_map distinct queries are padding up to a whole GEMM tile: they repeat the last one)
+  const int src_pair = pair_map != nullptr ? __ldg(pair_map + min(row / Lq, n_map - 1)) : row / Lq;
   Row x;
   row_load(x, E + int64_t(__ldg(query_ids + int64_t(src_pair) * Lq + s)) * kH, lane);
   row_add(x, P + int64_t(s) * kH, lane);
@@ -356,12 +357,12 @@ lx_lang_embed_kernel(const int32_t* __restrict__ query_ids, const int32_t* __res
 // Language stream computed once per distinct query (mmr_inputs.lang_unique / lang_slot): the compact key mask of the
 // representatives, and the expansion of the compact stream to all pairs before the cross-modality blocks.
 __global__ void __launch_bounds__(256)
-lx_gather_mask_kernel(const int32_t* __restrict__ mask, const int32_t* __restrict__ pair_map, int Lq, int n,
+lx_gather_mask_kernel(const int32_t* __restrict__ mask, const int32_t* __restrict__ pair_map, int n_map, int Lq, int n,
                       int32_t* __restrict__ out) {
   pdl_wait();
   pdl_launch_dependents();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = __ldg(mask + int64_t(__ldg(pair_map + i / Lq)) * Lq + i % Lq);
+  if (i < n) out[i] = __ldg(mask + int64_t(__ldg(pair_map + min(i / Lq, n_map - 1))) * Lq + i % Lq);
 }
 template <class E16>
 __global__ void __launch_bounds__(256)
@@ -611,16 +612,18 @@ mmr_status lds_embed(const int32_t* query_ids, const int32_t* segment_ids, const
 
 mmr_status lx_lang_embed(const int32_t* query_ids, const float* E, const float* T, const float* P,
                          const float* gamma, const float* beta, int Lq, int B, void* x16, float* x32, int dtype,
-                         cudaStream_t st, const int32_t* pair_map) {
-  const int rows = B * Lq;   // B = row groups written (distinct queries when pair_map is given)
+                         cudaStream_t st, const int32_t* pair_map, int n_map) {
+  const int rows = B * Lq;   // B = row groups written (with pair_map: the n_map distinct queries, padded by repetition)
   MMR_DISPATCH16(dtype, ((void)launch_pdl(lx_lang_embed_kernel<E16>, dim3(blocks_for(rows)), dim3(256), 0, st, 
-                            query_ids, pair_map, E, T, P, gamma, beta, Lq, rows, static_cast<typename E16::T*>(x16), x32)));
+                            query_ids, pair_map, n_map, E, T, P, gamma, beta, Lq, rows,
+                            static_cast<typename E16::T*>(x16), x32)));
   MMR_CUDA_OK(cudaGetLastError());
   return MMR_OK;
 }
-mmr_status lx_gather_mask(const int32_t* mask, const int32_t* pair_map, int Lq, int U, int32_t* out, cudaStream_t st) {
-  const int n = U * Lq;
-  (void)launch_pdl(lx_gather_mask_kernel, dim3((n + 255) / 256), dim3(256), 0, st, mask, pair_map, Lq, n, out);
+mmr_status lx_gather_mask(const int32_t* mask, const int32_t* pair_map, int n_map, int Lq, int groups, int32_t* out,
+                          cudaStream_t st) {
+  const int n = groups * Lq;
+  (void)launch_pdl(lx_gather_mask_kernel, dim3((n + 255) / 256), dim3(256), 0, st, mask, pair_map, n_map, Lq, n, out);
   MMR_CUDA_OK(cudaGetLastError());
   return MMR_OK;
 }

@@ -81,8 +81,9 @@ mmr_status lds_embed(const int32_t* query_ids, const int32_t* segment_ids, const
                      cudaStream_t st);
 mmr_status lx_lang_embed(const int32_t* query_ids, const float* E, const float* T, const float* P,
                          const float* gamma, const float* beta, int Lq, int B, void* x16, float* x32, int dtype,
-                         cudaStream_t st, const int32_t* pair_map = nullptr);
-mmr_status lx_gather_mask(const int32_t* mask, const int32_t* pair_map, int Lq, int U, int32_t* out, cudaStream_t st);
+                         cudaStream_t st, const int32_t* pair_map = nullptr, int n_map = 0);
+mmr_status lx_gather_mask(const int32_t* mask, const int32_t* pair_map, int n_map, int Lq, int groups, int32_t* out,
+                          cudaStream_t st);
 mmr_status lx_expand_rows(const float* src32, const void* src16, const int32_t* slot, int Lq, int B, float* dst32,
                           void* dst16, int dtype, cudaStream_t st);
 mmr_status lx_label_z(const int32_t* label_ids, const float* E, const float* T, const float* P,

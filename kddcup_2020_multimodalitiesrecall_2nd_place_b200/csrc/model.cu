@@ -697,14 +697,14 @@ struct Ctx {
              static_cast<uint8_t*>(out16) + int64_t(split) * ldo16 * 2, ldo16, nullptr, act);
   }
   mmr_status G_LN2(const void* A, int64_t lda, const Linear& W1, const Linear& W2, const LNp& ln1, const LNp& ln2,
-                   int rows, int split) {
+                   int rows, int split, int64_t row0 = 0) {
     if (mergeable(W1, W2, split) && gemm_ln_eligible(rows, W1.n, W1.k, dt)) {
-      MMR_TRY(gemm_ln_2w(A, lda, W1.w16, W2.w16, W1.k, rows, W1.k, W1.bias, W2.bias, x32(0), H, ln1.gamma, ln2.gamma,
-                         ln1.beta, ln2.beta, split, 1e-12f, x16(0), H, x32(0), H, dt, h->ln_table, st));
+      MMR_TRY(gemm_ln_2w(A, lda, W1.w16, W2.w16, W1.k, rows, W1.k, W1.bias, W2.bias, x32(row0), H, ln1.gamma, ln2.gamma,
+                         ln1.beta, ln2.beta, split, 1e-12f, x16(row0), H, x32(row0), H, dt, h->ln_table, st));
       return mark(K_GEMM, 2.0 * rows * W1.n * W1.k);
     }
-    MMR_TRY(G_LN(A, lda, W1, ln1, 0, split));
-    return G_LN(static_cast<const uint8_t*>(A) + int64_t(split) * lda * 2, lda, W2, ln2, split, rows - split);
+    MMR_TRY(G_LN(A, lda, W1, ln1, row0, split));
+    return G_LN(static_cast<const uint8_t*>(A) + int64_t(split) * lda * 2, lda, W2, ln2, row0 + split, rows - split);
   }
   mmr_status LN(float* x, const LNp& p, int rows, void* out16, float* out32, float scale, int accumulate) {
     MMR_TRY(layernorm(x, H, p.gamma, p.beta, 1e-12f, rows, H, out16, H, out32, H, scale, accumulate, dt, st));
@@ -725,21 +725,22 @@ static mmr_status attend(Ctx& c, int64_t q0, int Sq, int64_t k0, int Sk, const i
 // Two attention problems of one batch in ONE launch (LXMERT: both streams' self-attention, or both directions of the
 // shared cross-attention): saves a launch, a prologue and a tail of a kernel that is latency-bound at these shapes.
 static mmr_status attend2(Ctx& c, int64_t q0, int Sq0, int64_t k0, int Sk0, const int32_t* mask0, int64_t q1, int Sq1,
-                          int64_t k1, int Sk1, const int32_t* mask1, int B) {
+                          int64_t k1, int Sk1, const int32_t* mask1, int B, int B0 = 0) {
+  if (B0 <= 0) B0 = B;   // pairs of the FIRST problem (LXMERT with the language blocks once per query: fewer than B)
   static const bool env_off = [] { const char* e = getenv("MMR_LX_ATTN_PAIR"); return e != nullptr && atoi(e) == 0; }();
   bool separate = tuning(MMR_TUNE_LX_MERGE) == 0 || env_off;   // (environment: A/B measurements only)
 #ifdef MMR_EXPERIMENTAL
   separate = separate || tuning(MMR_TUNE_ATTN_TC) != 2;   // the older attention kernels take one problem per launch
 #endif
   if (separate) {
-    MMR_TRY(attend(c, q0, Sq0, k0, Sk0, mask0, B));
+    MMR_TRY(attend(c, q0, Sq0, k0, Sk0, mask0, B0));
     return attend(c, q1, Sq1, k1, Sk1, mask1, B);
   }
   const int64_t ld = 3 * int64_t(c.H);
-  const AttentionArgs a{c.qkv(q0, 0), c.qkv(k0, 1), c.qkv(k0, 2), ld, ld, ld, mask0, c.ctx(q0), c.H, B, Sq0, Sk0};
+  const AttentionArgs a{c.qkv(q0, 0), c.qkv(k0, 1), c.qkv(k0, 2), ld, ld, ld, mask0, c.ctx(q0), c.H, B0, Sq0, Sk0};
   const AttentionArgs b{c.qkv(q1, 0), c.qkv(k1, 1), c.qkv(k1, 2), ld, ld, ld, mask1, c.ctx(q1), c.H, B, Sq1, Sk1};
   MMR_TRY(attention_pair(a, b, c.h->cfg.heads, c.dt, c.st));
-  return c.mark(K_ATTENTION, 4.0 * B * (double(Sq0) * Sk0 + double(Sq1) * Sk1) * c.H);
+  return c.mark(K_ATTENTION, 4.0 * (double(B0) * Sq0 * Sk0 + double(B) * Sq1 * Sk1) * c.H);
 }
 // x = LN(ctx . Wo^T + bo + x), in place on the residual stream
 static mmr_status out_proj_ln(Ctx& c, const AttBlock& A, int64_t row0, int rows) {
@@ -764,15 +765,18 @@ static mmr_status bert_layer(Ctx& c, const Layer& L, int64_t row0, int B, int S,
 // One self-attention + FFN layer of BOTH LXMERT streams (language rows [0, nl), visual rows [nl, nl + nv)): the four
 // projections as merged launches, attention per stream.
 static mmr_status two_stream_att(Ctx& c, const AttBlock& A1, const AttBlock& A2, int B, int Lq, int R,
-                                 const int32_t* mask1, const int32_t* mask2) {
-  const int nl = B * Lq, nv = B * R;
-  MMR_TRY(c.G2(c.x16(0), c.H, A1.qkv, A2.qkv, nl + nv, nl, c.qkv(0, 0), 3 * c.H, MMR_ACT_NONE));
-  MMR_TRY(attend2(c, 0, Lq, 0, Lq, mask1, nl, R, nl, R, mask2, B));
-  return c.G_LN2(c.ctx(0), c.H, A1.out, A2.out, A1.ln, A2.ln, nl + nv, nl);
+                                 const int32_t* mask1, const int32_t* mask2, int64_t row0 = 0, int B1 = 0) {
+  // stream 1 = B1 row groups of Lq rows from row0 (all B pairs, or one group per distinct query), stream 2 = B x R rows
+  if (B1 <= 0) B1 = B;
+  const int nl = B1 * Lq, nv = B * R;
+  MMR_TRY(c.G2(c.x16(row0), c.H, A1.qkv, A2.qkv, nl + nv, nl, c.qkv(row0, 0), 3 * c.H, MMR_ACT_NONE));
+  MMR_TRY(attend2(c, row0, Lq, row0, Lq, mask1, row0 + nl, R, row0 + nl, R, mask2, B, B1));
+  return c.G_LN2(c.ctx(row0), c.H, A1.out, A2.out, A1.ln, A2.ln, nl + nv, nl, row0);
 }
-static mmr_status two_stream_ffn(Ctx& c, const FfnBlock& F1, const FfnBlock& F2, int nl, int nv) {
-  MMR_TRY(c.G2(c.x16(0), c.H, F1.in, F2.in, nl + nv, nl, c.h->h16, F1.in.n, c.h->act));
-  return c.G_LN2(c.h->h16, F1.in.n, F1.out, F2.out, F1.ln, F2.ln, nl + nv, nl);
+static mmr_status two_stream_ffn(Ctx& c, const FfnBlock& F1, const FfnBlock& F2, int nl, int nv, int64_t row0 = 0) {
+  uint8_t* hbuf = static_cast<uint8_t*>(c.h->h16) + row0 * F1.in.n * 2;
+  MMR_TRY(c.G2(c.x16(row0), c.H, F1.in, F2.in, nl + nv, nl, hbuf, F1.in.n, c.h->act));
+  return c.G_LN2(hbuf, F1.in.n, F1.out, F2.out, F1.ln, F2.ln, nl + nv, nl, row0);
 }
 
 // first token of every pair: rows b*S of x16 (row stride S*H), pixelbert.py:258-266 / modeling.py:596-608
@@ -899,12 +903,20 @@ static mmr_status forward_lxmert(Ctx& c, const mmr_inputs* in, int B, float* pro
   const int U = (tuning(MMR_TUNE_LX_QUERY_DEDUP) != 0 && h->keep_taps == 0 && in->lang_unique != nullptr &&
                  in->lang_slot != nullptr && in->n_lang_unique > 0 && in->n_lang_unique < B && !h->layers.empty())
                     ? in->n_lang_unique : 0;
+  // With query grouping, the compact language stream can ride the merged two-stream launches when it is padded to
+  // whole 256-row tiles (groups beyond U repeat the last distinct query): it then sits in the main buffers right BEFORE
+  // the visual rows, [v0 - nlp, v0) -- rows that belong to the expanded language stream only after the language blocks.
+  const int nlp = U > 0 ? ((U * Lq + 255) / 256) * 256 : 0;
+  const bool ride = U > 0 && tuning(MMR_TUNE_LX_MERGE) != 0 && nlp % Lq == 0 && nlp <= nl && !h->r_layers.empty();
+  const int Up = ride ? nlp / Lq : U;                    // language row groups actually computed
+  const int64_t r0 = ride ? v0 - nlp : 0;                // first row of the compact language stream
   // language embedding (modeling.py:913)
   if (U > 0) {
-    MMR_TRY(lx_lang_embed(in->query_ids, h->E, h->T, h->P, h->emb_ln.gamma, h->emb_ln.beta, Lq, U, h->xl16c, h->xl32c, c.dt,
-                          c.st, in->lang_unique));
+    MMR_TRY(lx_lang_embed(in->query_ids, h->E, h->T, h->P, h->emb_ln.gamma, h->emb_ln.beta, Lq, Up,
+                          ride ? static_cast<void*>(c.x16(r0)) : h->xl16c, ride ? c.x32(r0) : h->xl32c, c.dt, c.st,
+                          in->lang_unique, U));
     MMR_TRY(c.mark(K_ROW, 0));
-    MMR_TRY(lx_gather_mask(in->query_mask, in->lang_unique, Lq, U, h->lang_mask_c, c.st));
+    MMR_TRY(lx_gather_mask(in->query_mask, in->lang_unique, U, Lq, Up, h->lang_mask_c, c.st));
   } else {
     MMR_TRY(lx_lang_embed(in->query_ids, h->E, h->T, h->P, h->emb_ln.gamma, h->emb_ln.beta, Lq, B, c.x16(0), c.x32(0),
                           c.dt, c.st));
@@ -928,9 +940,22 @@ static mmr_status forward_lxmert(Ctx& c, const mmr_inputs* in, int B, float* pro
   // language layers (modeling.py:577-578) and visual layers (:582-583) are independent chains: the first
   // min(9, 5) of each run pairwise through merged launches, the rest alone
   const bool merge = tuning(MMR_TUNE_LX_MERGE) != 0 && nl % 256 == 0;
-  if (U > 0) {
-    // the language-only blocks (modeling.py:577-578) on the compact stream, the visual ones (:582-583) on theirs, then
-    // every pair receives its query's rows
+  if (U > 0 && ride) {
+    // language blocks (modeling.py:577-578) and visual blocks (:582-583) pairwise through the merged launches, the
+    // rest alone; then the compact stream moves aside and every pair receives its query's rows
+    const size_t both = std::min(h->layers.size(), h->r_layers.size());
+    for (size_t i = 0; i < both; ++i) {
+      MMR_TRY(two_stream_att(c, h->layers[i].att, h->r_layers[i].att, B, Lq, R, h->lang_mask_c, in->visn_mask, r0, Up));
+      MMR_TRY(two_stream_ffn(c, h->layers[i].ffn, h->r_layers[i].ffn, nlp, nv, r0));
+    }
+    for (size_t i = both; i < h->layers.size(); ++i) MMR_TRY(bert_layer(c, h->layers[i], r0, Up, Lq, h->lang_mask_c));
+    for (size_t i = both; i < h->r_layers.size(); ++i) MMR_TRY(bert_layer(c, h->r_layers[i], v0, B, R, in->visn_mask));
+    MMR_CUDA_OK(cudaMemcpyAsync(h->xl32c, c.x32(r0), size_t(U) * Lq * H * 4, cudaMemcpyDeviceToDevice, c.st));
+    MMR_CUDA_OK(cudaMemcpyAsync(h->xl16c, c.x16(r0), size_t(U) * Lq * H * 2, cudaMemcpyDeviceToDevice, c.st));
+    MMR_TRY(lx_expand_rows(h->xl32c, h->xl16c, in->lang_slot, Lq, B, c.x32(0), c.x16(0), c.dt, c.st));
+    MMR_TRY(c.mark(K_ROW, 0));
+  } else if (U > 0) {
+    // the language-only blocks on the compact stream in its own buffers, the visual ones on theirs
     Ctx cl = c;
     cl.x16_base = h->xl16c;
     cl.x32_base = h->xl32c;
