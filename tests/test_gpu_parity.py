@@ -330,6 +330,9 @@ def test_lxmert_two_stream_merged_launches(B, lq):
     sc = _scorer(cfg, w, B)
     try:
         out, launches = {}, {}
+        # (query grouping off: with it the language stream takes a different route in the two modes -- riding the merged
+        # launches vs its own small ones -- and this test is about the launches themselves)
+        _lib.check(lib.mmr_set_tuning(_lib.TUNE_LX_QUERY_DEDUP, 0))
         for merged in (1, 0):
             _lib.check(lib.mmr_set_tuning(_lib.TUNE_LX_MERGE, merged))
             out[merged], _ = _gpu_probs(sc, inp)
@@ -340,6 +343,7 @@ def test_lxmert_two_stream_merged_launches(B, lq):
         assert (out[1] - _oracle(cfg, w, inp)["probs"]).abs().max().item() <= TOL
     finally:
         _lib.check(lib.mmr_set_tuning(_lib.TUNE_LX_MERGE, 1))
+        _lib.check(lib.mmr_set_tuning(_lib.TUNE_LX_QUERY_DEDUP, 1))
         sc.close()
 
 

@@ -507,6 +507,7 @@ def test_lxmert_paired_attention_launch_is_bit_identical():
         sc = _scorer(cfg, w, B)
         try:
             out, launches = {}, {}
+            _lib.check(lib.mmr_set_tuning(_lib.TUNE_LX_QUERY_DEDUP, 0))     # the same route for the language stream in both modes
             for merged in (1, 0):
                 _lib.check(lib.mmr_set_tuning(_lib.TUNE_LX_MERGE, merged))
                 _lib.check(lib.mmr_set_tuning(_lib.TUNE_PRUNE_LAST, 0))     # every attention pair of the graph
@@ -518,6 +519,7 @@ def test_lxmert_paired_attention_launch_is_bit_identical():
         finally:
             _lib.check(lib.mmr_set_tuning(_lib.TUNE_LX_MERGE, 1))
             _lib.check(lib.mmr_set_tuning(_lib.TUNE_PRUNE_LAST, 1))
+            _lib.check(lib.mmr_set_tuning(_lib.TUNE_LX_QUERY_DEDUP, 1))
             sc.close()
 
 
@@ -548,7 +550,7 @@ def test_lxmert_language_blocks_once_per_distinct_query(B, nq, full):
         d = (out[0] - out[1]).abs().max().item()
         print(f"lxmert B={B}, {len(uniq)} distinct queries: dedup vs per-pair max|dscore| = {d:.2e}; launches "
               f"{launches[1]} vs {launches[0]}")
-        if len(uniq) * cfg.lq > 128 and len(uniq) < B:
+        if len(uniq) < B:      # the compact stream rides the merged launches (padded to whole tiles): same kernels, same bits
             assert torch.equal(out[0], out[1])
         assert d <= 4e-4
         if not full:
