@@ -184,10 +184,6 @@ struct mmr_handle {
   void* a16s = nullptr;          // [rows, 3 K] split A operand of the GEMM being launched
   float *qkv32 = nullptr, *ctx32 = nullptr, *h32 = nullptr;
   cudaEvent_t done_ev = nullptr; // recorded after every eager forward: cross-stream serialisation on one device
-  // zk: the label-term kernels depend on the label ids only; they run on a side stream next to the feature cast and
-  // the region projection (fork / join by events: capturable into the same CUDA graph)
-  cudaStream_t side = nullptr;
-  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
   int64_t rows_max = 0;   // encoder rows at max_batch
   int last_B = 0;
   int pruned_last = 0;   // the last forward computed its final block for the [CLS] rows only
@@ -618,11 +614,6 @@ static mmr_status alloc_workspace(mmr_handle* h, size_t* size_only = nullptr) {
     MMR_CUDA_OK(cudaMemcpy(h->lab_epoch_dev, &first_epoch, sizeof(first_epoch), cudaMemcpyHostToDevice));
   }
   MMR_CUDA_OK(cudaEventCreateWithFlags(&h->done_ev, cudaEventDisableTiming));
-  if (zk) {
-    MMR_CUDA_OK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
-    MMR_CUDA_OK(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
-    MMR_CUDA_OK(cudaEventCreateWithFlags(&h->join_ev, cudaEventDisableTiming));
-  }
   MMR_CUDA_OK(cudaDeviceSynchronize());
   return MMR_OK;
 }
@@ -833,20 +824,6 @@ static mmr_status forward_single_stream(Ctx& c, const mmr_inputs* in, int B, flo
   const bool fused_in = zk && in->region_sum != nullptr;
   MMR_REQUIRE(in->query_ids && in->segment_ids && (fused_in || (in->label_ids && in->feats)),
               "mmr_forward: missing input pointer");
-  // zk: label term once per distinct phrase (the claim kernel reads the 8 ids of a box as two 16-byte words); its two
-  // kernels need the label ids only, so they are forked onto the side stream here and joined before the per-box sum
-  // (not while per-launch profiling events are being recorded on the forward's stream)
-  const bool label_dedup = zk && !fused_in && tuning(MMR_TUNE_LABEL_DEDUP) != 0 && in->label_ids != nullptr &&
-                           (reinterpret_cast<uintptr_t>(in->label_ids) & 15) == 0;
-  static const bool fork_off = [] { const char* e = getenv("MMR_LABEL_FORK"); return e != nullptr && atoi(e) == 0; }();
-  const bool forked = label_dedup && h->side != nullptr && !h->prof_on && !fork_off;   // (environment: A/B runs only)
-  if (forked) {
-    MMR_CUDA_OK(cudaEventRecord(h->fork_ev, c.st));
-    MMR_CUDA_OK(cudaStreamWaitEvent(h->side, h->fork_ev, 0));
-    MMR_TRY(zk_label_terms(in->label_ids, h->tables, cfg.vocab, h->bc1, h->lab_tab, h->lab_tab_mask, h->lab_epoch_dev,
-                           h->lab_rep, h->lab_term32, B * R, h->side));
-    MMR_CUDA_OK(cudaEventRecord(h->join_ev, h->side));
-  }
   if (!fused_in) {
     MMR_TRY(cast16(in->feats, h->f16, int64_t(B) * R * cfg.feat_dim, c.dt, c.st));
     MMR_TRY(c.mark(K_ROW, 0));
@@ -862,12 +839,10 @@ static mmr_status forward_single_stream(Ctx& c, const mmr_inputs* in, int B, flo
     } else {
       // feat = ReLU(f . Wc2 + bc2)  (model_triple.py:192-194)
       MMR_TRY(c.G(h->f16, cfg.feat_dim, h->conv2, B * R, nullptr, nullptr, 0, h->tmp32, MMR_ACT_RELU));
-      if (label_dedup) {
-        if (forked)
-          MMR_CUDA_OK(cudaStreamWaitEvent(c.st, h->join_ev, 0));
-        else
-          MMR_TRY(zk_label_terms(in->label_ids, h->tables, cfg.vocab, h->bc1, h->lab_tab, h->lab_tab_mask,
-                                 h->lab_epoch_dev, h->lab_rep, h->lab_term32, B * R, c.st));
+      // (the claim kernel reads the 8 ids of a box as two 16-byte words)
+      if (tuning(MMR_TUNE_LABEL_DEDUP) != 0 && (reinterpret_cast<uintptr_t>(in->label_ids) & 15) == 0) {
+        MMR_TRY(zk_label_terms(in->label_ids, h->tables, cfg.vocab, h->bc1, h->lab_tab, h->lab_tab_mask, h->lab_epoch_dev,
+                               h->lab_rep, h->lab_term32, B * R, c.st));
         MMR_TRY(c.mark(K_ROW, 0));
         MMR_TRY(c.mark(K_ROW, 0));
         MMR_TRY(zk_region_sum_rep(h->tmp32, in->boxes, h->lab_rep, h->lab_term32, h->Wb, h->bb, h->t16, B * R,
@@ -1311,9 +1286,6 @@ extern "C" void mmr_destroy(mmr_handle* h) {
     if (h->device >= 0 && h->device < 64 && mmr::g_tail[h->device].owner == h) mmr::g_tail[h->device] = mmr::DeviceTail();
   }
   if (h->done_ev) cudaEventDestroy(h->done_ev);
-  if (h->fork_ev) cudaEventDestroy(h->fork_ev);
-  if (h->join_ev) cudaEventDestroy(h->join_ev);
-  if (h->side) cudaStreamDestroy(h->side);
   if (h->weights.base) cudaFree(h->weights.base);
   if (h->work.base) cudaFree(h->work.base);
   if (h->layer_tap) cudaFree(h->layer_tap);
