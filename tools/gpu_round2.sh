@@ -18,3 +18,6 @@ for k, v in (d["other_models"] or {}).items():
 print(d["strict"]); print(d["cfg4"]); print(d["cfg5"]); print(d["cpu_baseline"])
 PY
 timeout 300 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_reference.json; cut -c1-300 gpurun_out/${TAG}_bench_reference.json
+# ncu launch list of the same bench command (every launch; the summary keeps the last two forwards = the step's kernels)
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --quick --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_under_ncu.log 2>&1; echo "launch list rc=$?"
+python tools/summarize_launches.py gpurun_out/${TAG}_launches.csv -138 | tee gpurun_out/${TAG}_launches_step.txt

@@ -1,6 +1,9 @@
 """Summarises an `ncu --metrics gpu__time_duration.sum --csv` launch list per kernel (count, total us, share).
 
-    python tools/summarize_launches.py gpurun_out/launches.csv [skip_first_n]
+    python tools/summarize_launches.py gpurun_out/launches.csv [skip_first_n | -last_n]
+
+A negative second argument keeps only the LAST n launches: with `bench.py --quick --no-e2e --no-cpu-baseline` the list
+ends with whole forwards (timed steps, then the event-profiled ones), so `-138` = two 69-launch forwards of the step.
 """
 import collections
 import csv
@@ -18,7 +21,7 @@ def main():
                 hdr = r
             continue
         data.append(dict(zip(hdr, r)))
-    data = data[skip:]
+    data = data[skip:]      # (a negative value slices from the end)
     agg = collections.OrderedDict()
     for d in data:
         name = re.sub(r"\(.*", "", d["Kernel Name"])[:80]
