@@ -72,7 +72,6 @@ struct GemmLnParams {
   uint32_t* epoch;        // [0] tag of this launch (read at kernel start), [1] CTAs finished; the last CTA bumps [0]
   uint32_t idesc_fmt;
   unsigned long long* trace;   // debug: per (CTA, epilogue warp, tile) phase timestamps in ns, or null
-  int descending;              // walk the row blocks from the last one down (see gemm_ln_2w)
 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -149,11 +148,9 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (lane == 0) {
       RingPos pos;
       const int w_row = n_tile * kBN + int(rank) * (kBN / 2);
-      for (int b = group; b < m_tiles; b += n_groups) {
-        const int m_blk = p.descending ? m_tiles - 1 - b : b;
+      for (int m_blk = group; m_blk < m_tiles; m_blk += n_groups)
         pair_produce_tile<kLnStages, 1>(ring, pos, &tmap_a, m_blk >= p.split_blk ? &tmap_w2 : &tmap_w,
                                         m_blk * kPairRows + int(rank) * kCtaRows, w_row, kBN / 2, k_blocks, rank, 0, 0);
-      }
     }
   } else if (warp == kLnMmaWarp) {
     // ===================== MMA issuer (pair leader, one thread) =====================
@@ -188,7 +185,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ---- pass 1 of this warp's `it`-th tile: y = acc + bias + residual -> back into TMEM; shifted sums (shift = this
     // thread's first y); publish (mean_i, M2_i) of the thread's 128 columns
     auto pass1 = [&](int it) {
-      const int m_blk = p.descending ? m_tiles - 1 - (group + it * n_groups) : group + it * n_groups;
+      const int m_blk = group + it * n_groups;
       const int acc = it & 1;
       const float* bias_w = vec_w + (m_blk >= p.split_blk ? 3 * kBN : 0);
       const int row0 = m_blk * kPairRows + row_in_blk;
@@ -251,7 +248,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ---- exchange + pass 2 of the `it`-th tile: wait for the 6 partials of this thread's row, Chan's formula,
     // normalise from TMEM, affine, swizzled stages, TMA stores
     auto pass2 = [&](int it) {
-      const int m_blk = p.descending ? m_tiles - 1 - (group + it * n_groups) : group + it * n_groups;
+      const int m_blk = group + it * n_groups;
       const int acc = it & 1;
       const float* bias_w = vec_w + (m_blk >= p.split_blk ? 3 * kBN : 0);
       const float* gamma_w = bias_w + kBN;
@@ -488,13 +485,9 @@ mmr_status gemm_ln_2w(const void* A16, int64_t lda, const void* W16, const void*
   MMR_TRY(make_tmap_ex(&tr, residual, M, kLnN, ldr, 2, 32, 32, 128));
   MMR_TRY(make_tmap_ex(&to32, out32, M, kLnN, ldo32, 2, 32, 32, 128));
   MMR_TRY(make_tmap_ex(&to16, out16, M, kLnN, ldo16, ek, 32, 32, 64));
-  // FFN-out reads the GELU(FFN-in) rows the previous launch wrote in ascending order, 107 MB at cfg2 -- nearly the whole
-  // L2: walking the row blocks from the LAST one down meets the most recently written rows while they are still
-  // resident instead of the ones already evicted (environment MMR_LN_DESCENDING=0: ascending, for A/B runs)
-  static const bool desc_off = [] { const char* e = getenv("MMR_LN_DESCENDING"); return e != nullptr && atoi(e) == 0; }();
   GemmLnParams p{M, K, bias, gamma, beta, two ? biasb : bias, two ? gammab : gamma, two ? betab : beta,
                  two ? split_row / kPairRows : 0x7fffffff, eps, static_cast<uint4*>(table.stats), table.epoch,
-                 uint32_t(dtype), g_ln_trace, (K > 1024 && !desc_off) ? 1 : 0};
+                 uint32_t(dtype), g_ln_trace};
   if (dtype == MMR_DT_BF16) return launch_ln<BF16>(ta, tw, tw2, tr, to32, to16, p, stream);
   return launch_ln<FP16>(ta, tw, tw2, tr, to32, to16, p, stream);
 }
