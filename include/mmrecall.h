@@ -142,6 +142,14 @@ typedef struct {
 } mmr_decode_out;
 mmr_status mmr_decode_tsv(const char* const* lines, const size_t* line_len, int64_t n_lines, const mmr_decode_out* out,
                           int n_threads);
+/* The same for batch arrays that are decoded into again and again (a driver's pinned staging arrays): dirty_boxes
+ * [n_lines] is caller-kept state, one count per record slot of the arrays = how many leading box slots may hold
+ * non-zero data (initialise to -1 or max_boxes for arrays of unknown content, 0 for zero-filled ones).  Only the slots
+ * [boxes of this record, dirty) are cleared and the count is updated, instead of zero-padding every record to
+ * max_boxes: at 36 slots and ~4 boxes per record the padding is 90 % of the bytes (seq_padding_2's job,
+ * load_data_v4.py:91-102).  The arrays end up byte-identical to mmr_decode_tsv's. */
+mmr_status mmr_decode_tsv_reuse(const char* const* lines, const size_t* line_len, int64_t n_lines,
+                                const mmr_decode_out* out, int32_t* dirty_boxes, int n_threads);
 /* CRC-32C (Castagnoli) of a HOST buffer, continuing from `crc` (0 to start): the per-block / per-tensor checksum of
  * the TensorFlow checkpoints the two ImageBert drivers restore (imagebert_zk/evaluate_normal.py:204-212,
  * imagebert_lds/src/run_pretraining_predict_score.py:347-362); used by the pure-Python bundle reader. */

@@ -17,7 +17,7 @@ PRECISION_FAST, PRECISION_STRICT = 0, 1
 # every symbol include/mmrecall.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "mmr_last_error", "mmr_abi_version", "mmr_experimental_build", "mmr_device_check", "mmr_set_tuning", "mmr_get_tuning", "mmr_tuning_generation",
-    "mmr_gemm", "mmr_gemm_layernorm", "mmr_gemm_layernorm_supported", "mmr_layernorm", "mmr_attention", "mmr_cast16", "mmr_cls_attention", "mmr_split3", "mmr_attention_f32", "mmr_am_softmax_head", "mmr_linear_head", "mmr_decode_tsv", "mmr_crc32c", "mmr_boxes_normalize", "mmr_ensemble_topk", "mmr_ndcg_at_k",
+    "mmr_gemm", "mmr_gemm_layernorm", "mmr_gemm_layernorm_supported", "mmr_layernorm", "mmr_attention", "mmr_cast16", "mmr_cls_attention", "mmr_split3", "mmr_attention_f32", "mmr_am_softmax_head", "mmr_linear_head", "mmr_decode_tsv", "mmr_decode_tsv_reuse", "mmr_crc32c", "mmr_boxes_normalize", "mmr_ensemble_topk", "mmr_ndcg_at_k",
     "mmr_create", "mmr_workspace_bytes", "mmr_destroy", "mmr_forward", "mmr_set_debug_taps", "mmr_get_activation",
     "mmr_launches_per_forward", "mmr_set_profiling", "mmr_get_profile",
 ]

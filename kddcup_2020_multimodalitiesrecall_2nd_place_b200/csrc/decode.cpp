@@ -10,9 +10,14 @@
 #include <atomic>
 #include <cstdint>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
+
+#include <unistd.h>
 
 #include "../../include/mmrecall.h"
 
@@ -91,7 +96,10 @@ bool parse_i64(const char* p, size_t n, int64_t* out) {
 // error codes stored per line
 enum { kOk = 0, kColumns = 1, kNumber = 2, kBase64 = 3, kTooManyBoxes = 4, kQueryOverflow = 5 };
 
-int decode_line(const char* line, size_t len, const mmr_decode_out& o, int64_t i, std::atomic<size_t>& qcursor) {
+// `dirty` (or null): in/out count of leading box slots of record i that may hold non-zero data from an earlier decode
+// into the same arrays; with it, only the slots [keep, dirty) are zeroed instead of all of [keep, R).
+int decode_line(const char* line, size_t len, const mmr_decode_out& o, int64_t i, std::atomic<size_t>& qcursor,
+                int32_t* dirty) {
   while (len > 0 && (line[len - 1] == '\n' || line[len - 1] == '\r' || line[len - 1] == ' ')) --len;   // .strip()
   while (len > 0 && (*line == ' ' || *line == '\n')) { ++line; --len; }
   const char* f[9];
@@ -115,6 +123,7 @@ int decode_line(const char* line, size_t len, const mmr_decode_out& o, int64_t i
   // the reference truncates to the box budget AFTER decoding (seq_padding_2: x[:maxlen]); decode straight into place
   // when everything fits, else through a scratch buffer
   const int keep = int(std::min<int64_t>(nb, R));
+  if (dirty && dirty[i] >= 0 && dirty[i] < keep) dirty[i] = keep;   // (stays valid if this record fails half-way)
   float* boxes = o.boxes4 + size_t(i) * R * 4;
   float* feats = o.feats + size_t(i) * R * F;
   int64_t* labels = o.class_labels + size_t(i) * R;
@@ -132,10 +141,13 @@ int decode_line(const char* line, size_t len, const mmr_decode_out& o, int64_t i
     if (b64_decode(f[6], fl[6], tmp.data(), size_t(nb) * 8) != long(nb) * 8) return kBase64;
     memcpy(labels, tmp.data(), size_t(keep) * 8);
   }
-  // zero padding of the unused box slots (seq_padding_2(..., padding_value=0))
-  memset(boxes + size_t(keep) * 4, 0, size_t(R - keep) * 16);
-  memset(feats + size_t(keep) * F, 0, size_t(R - keep) * F * 4);
-  memset(labels + keep, 0, size_t(R - keep) * 8);
+  // zero padding of the unused box slots (seq_padding_2(..., padding_value=0)); at 36 slots of 8 KB and 4 boxes per
+  // record the padding is 90 % of the bytes a record occupies, so a reused array is only cleared where it is not zero
+  const int stale = dirty ? std::max(keep, std::min<int>(R, dirty[i] < 0 ? R : dirty[i])) : R;
+  memset(boxes + size_t(keep) * 4, 0, size_t(stale - keep) * 16);
+  memset(feats + size_t(keep) * F, 0, size_t(stale - keep) * F * 4);
+  memset(labels + keep, 0, size_t(stale - keep) * 8);
+  if (dirty) dirty[i] = keep;
   o.product_id[i] = pid;
   o.image_h[i] = int32_t(h);
   o.image_w[i] = int32_t(w);
@@ -149,10 +161,65 @@ int decode_line(const char* line, size_t len, const mmr_decode_out& o, int64_t i
   return kOk;
 }
 
-}  // namespace
 
-extern "C" mmr_status mmr_decode_tsv(const char* const* lines, const size_t* line_len, int64_t n_lines,
-                                     const mmr_decode_out* out, int n_threads) {
+
+// Worker threads that outlive a call: a 256-line batch decodes in about a millisecond on 16 threads, which is what
+// creating and joining 15 threads costs.  One job at a time (calls are serialised); a forked child starts its own pool.
+class DecodePool {
+ public:
+  void run(int helpers, const std::function<void()>& job) {
+    std::lock_guard<std::mutex> serial(run_mu_);
+    std::unique_lock<std::mutex> lk(mu_);
+    if (pid_ != getpid()) {            // after fork() the parent's threads do not exist here: forget their handles
+      threads_ = new std::vector<std::thread>();
+      pid_ = getpid();
+    }
+    while (int(threads_->size()) < helpers) threads_->emplace_back([this, id = int(threads_->size())] { loop(id); });
+    job_ = &job;
+    want_ = helpers;
+    pending_ = helpers;
+    ++gen_;
+    lk.unlock();
+    cv_work_.notify_all();
+    job();
+    lk.lock();
+    cv_done_.wait(lk, [this] { return pending_ == 0; });
+    job_ = nullptr;
+  }
+
+ private:
+  void loop(int id) {
+    uint64_t seen = 0;
+    std::unique_lock<std::mutex> lk(mu_);
+    for (;;) {
+      cv_work_.wait(lk, [&] { return stop_ || gen_ != seen; });
+      if (stop_) return;
+      seen = gen_;
+      if (id >= want_) continue;       // this job asked for fewer threads
+      const std::function<void()>* job = job_;
+      lk.unlock();
+      (*job)();
+      lk.lock();
+      if (--pending_ == 0) cv_done_.notify_one();
+    }
+  }
+  std::mutex run_mu_, mu_;
+  std::condition_variable cv_work_, cv_done_;
+  std::vector<std::thread>* threads_ = new std::vector<std::thread>();
+  const std::function<void()>* job_ = nullptr;
+  uint64_t gen_ = 0;
+  int want_ = 0, pending_ = 0;
+  bool stop_ = false;
+  pid_t pid_ = getpid();
+};
+
+DecodePool& decode_pool() {
+  static DecodePool* pool = new DecodePool();    // never destroyed: its threads sleep on a condition variable until exit()
+  return *pool;
+}
+
+mmr_status decode_tsv(const char* const* lines, const size_t* line_len, int64_t n_lines, const mmr_decode_out* out,
+                      int32_t* dirty, int n_threads) {
   if (!lines || !line_len || !out || n_lines < 0)
     return mmr::fail(MMR_ERR_INVALID, "mmr_decode_tsv: null argument");
   const mmr_decode_out& o = *out;
@@ -160,26 +227,23 @@ extern "C" mmr_status mmr_decode_tsv(const char* const* lines, const size_t* lin
       !o.query_id || !o.query_off || !o.query_text || o.max_boxes <= 0 || o.feat_dim <= 0)
     return mmr::fail(MMR_ERR_INVALID, "mmr_decode_tsv: incomplete output descriptor");
   if (n_threads <= 0) n_threads = int(std::max(1u, std::thread::hardware_concurrency()));
-  n_threads = int(std::min<int64_t>(n_threads, std::max<int64_t>(n_lines, 1)));
+  n_threads = int(std::min<int64_t>(std::min(n_threads, 256), std::max<int64_t>(n_lines, 1)));
   std::atomic<int64_t> next(0);
   std::atomic<size_t> qcursor(0);
   std::atomic<int64_t> first_bad(-1);
   std::atomic<int> bad_code(0);
-  auto work = [&]() {
+  const std::function<void()> work = [&]() {
     for (;;) {
       const int64_t i = next.fetch_add(1);
       if (i >= n_lines) return;
-      const int rc = decode_line(lines[i], line_len[i], o, i, qcursor);
+      const int rc = decode_line(lines[i], line_len[i], o, i, qcursor, dirty);
       if (rc != kOk) {
         int64_t expect = -1;
         if (first_bad.compare_exchange_strong(expect, i)) bad_code.store(rc);
       }
     }
   };
-  std::vector<std::thread> pool;
-  for (int t = 1; t < n_threads; ++t) pool.emplace_back(work);
-  work();
-  for (auto& th : pool) th.join();
+  if (n_threads > 1) decode_pool().run(n_threads - 1, work); else work();
   if (first_bad.load() >= 0) {
     static const char* what[] = {"", "fewer than 9 tab-separated columns", "malformed integer field",
                                  "malformed or wrong-sized base64 field", "more than 4096 boxes",
@@ -187,6 +251,19 @@ extern "C" mmr_status mmr_decode_tsv(const char* const* lines, const size_t* lin
     return mmr::fail(MMR_ERR_INVALID, "mmr_decode_tsv: line %lld: %s", (long long)first_bad.load(), what[bad_code.load()]);
   }
   return MMR_OK;
+}
+
+}  // namespace
+
+extern "C" mmr_status mmr_decode_tsv(const char* const* lines, const size_t* line_len, int64_t n_lines,
+                                     const mmr_decode_out* out, int n_threads) {
+  return decode_tsv(lines, line_len, n_lines, out, nullptr, n_threads);
+}
+
+extern "C" mmr_status mmr_decode_tsv_reuse(const char* const* lines, const size_t* line_len, int64_t n_lines,
+                                           const mmr_decode_out* out, int32_t* dirty_boxes, int n_threads) {
+  if (!dirty_boxes) return mmr::fail(MMR_ERR_INVALID, "mmr_decode_tsv_reuse: null dirty_boxes");
+  return decode_tsv(lines, line_len, n_lines, out, dirty_boxes, n_threads);
 }
 
 // CRC-32C (Castagnoli) of a host buffer, continuing from `crc` (0 to start): the checksum TensorFlow checkpoints carry

@@ -57,8 +57,9 @@ def distinct_queries(query_ids, query_mask):
     [B, lq] integers."""
     q = query_ids.numpy() if torch.is_tensor(query_ids) else np.asarray(query_ids)
     m = query_mask.numpy() if torch.is_tensor(query_mask) else np.asarray(query_mask)
-    key = np.concatenate([q.astype(np.int64), m.astype(np.int64)], axis=1)
-    _, first, inverse = np.unique(key, axis=0, return_index=True, return_inverse=True)
+    key = np.ascontiguousarray(np.concatenate([q.astype(np.int32), m.astype(np.int32)], axis=1))
+    rows = key.view(np.dtype((np.void, key.shape[1] * 4))).ravel()      # one opaque item per row: a 1-D unique
+    _, first, inverse = np.unique(rows, return_index=True, return_inverse=True)
     order = np.argsort(first, kind="stable")              # representatives in ascending pair order
     rank = np.empty_like(order)
     rank[order] = np.arange(len(order))
@@ -325,7 +326,19 @@ class MatchScorer:
                 if i >= 2:
                     copy.wait_event(s["free"])            # kernels of chunk i-2 have consumed this slot
                 for name in self.spec:
-                    s["dev"][name][: hi - lo].copy_(chunk[name], non_blocking=True)
+                    src = chunk[name]
+                    if not src.is_cuda and not src.is_pinned():
+                        # a copy from pageable memory blocks the host until the copy stream gets to it (i.e. until the
+                        # kernels two chunks back are done): go through the slot's pinned staging instead
+                        stage = s["host"].get(name)
+                        if stage is None:
+                            dt, shape = self.spec[name]
+                            stage = s["host"][name] = torch.empty((Bm, *shape), dtype=dt).pin_memory()
+                        # (numpy: a torch copy_ of this size wakes the intra-op thread pool, whose workers then spin
+                        # on every core for a while -- under the feet of a driver's decoder threads)
+                        np.copyto(stage.numpy()[: hi - lo], src.detach().numpy(), casting="unsafe")
+                        src = stage[: hi - lo]
+                    s["dev"][name][: hi - lo].copy_(src, non_blocking=True)
                 if group is not None:
                     s["dev"]["lang_unique"][: group[0].shape[0]].copy_(group[0], non_blocking=True)
                     s["dev"]["lang_slot"][: hi - lo].copy_(group[1], non_blocking=True)

@@ -176,6 +176,57 @@ def test_decode_edge_cases_and_errors():
     assert len(ok["queries"]) == 2
 
 
+def test_reused_decoder_arrays_equal_a_fresh_decode():
+    """RecordDecoder clears only the box slots an earlier batch left non-zero (mmr_decode_tsv_reuse): whatever was
+    decoded into the arrays before -- more boxes, fewer lines, a batch that failed half-way, concurrent callers of the
+    thread pool -- the arrays must be byte-identical to a one-shot decode of the same lines."""
+    import threading
+
+    from kddcup_2020_multimodalitiesrecall_2nd_place_b200._lib import MmrError
+    rng = np.random.default_rng(11)
+    R = 12
+    big, _ = _make_lines(9, rng, max_nb=20)               # some records over the box budget
+    small, _ = _make_lines(9, rng, max_nb=3)
+    mid, _ = _make_lines(5, rng, max_nb=9)
+    dec = records.RecordDecoder(9, max_boxes=R, n_threads=3, pin=False)
+    keys = ("product_id", "image_h", "image_w", "num_boxes", "boxes4", "feats", "class_labels", "query_id")
+
+    def check(lines):
+        got = dec.decode(lines)
+        want = records.decode_lines(lines, max_boxes=R, n_threads=1, pin=False)
+        for k in keys:
+            assert torch.equal(got[k], want[k]), k
+        assert got["queries"] == want["queries"]
+
+    for lines in (big, small, mid, big[::-1], small):
+        check(lines)
+    cols = big[2].split(b"\t")
+    cols[5] = cols[5][:-8]                                  # fails after its boxes and part of its features were written
+    with pytest.raises(MmrError, match="base64"):
+        dec.decode([big[0], big[1], b"\t".join(cols)])
+    check(small)
+    check(mid)
+    # several decoders at once on the shared worker pool
+    errs = []
+
+    def worker(seed):
+        try:
+            r = np.random.default_rng(seed)
+            d = records.RecordDecoder(6, max_boxes=R, n_threads=4, pin=False)
+            for _ in range(4):
+                ls, _ = _make_lines(int(r.integers(1, 7)), r, max_nb=14)
+                got = d.decode(ls)
+                want = records.decode_lines(ls, max_boxes=R, n_threads=1, pin=False)
+                assert all(torch.equal(got[k], want[k]) for k in keys)
+        except Exception as e:                              # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=worker, args=(s,)) for s in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+
+
 def test_feed_assembly_follows_the_loaders():
     """Token ids / lengths / masks / label phrases as load_data_v4.py:148-163, 204, 259-265 and utils.py:38-59 build them."""
     k = _kat()
