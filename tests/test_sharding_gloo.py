@@ -90,6 +90,64 @@ def test_two_gloo_ranks_shard_gather_and_ensemble(n, tmp_path):
     assert len(r0) == len(r1) and all(list(a) == list(b) for a, b in zip(r0, r1))
 
 
+class _StandInTsvScorer:
+    """What drivers.score_tsv touches of a MatchScorer: cfg, max_batch, device, copy_stream, score_stream."""
+    device = torch.device("cpu")
+    copy_stream = None                      # torch.cuda.stream(None) is a no-op
+    max_batch = 4
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+        self.fetched = []
+
+    def score_stream(self, n, fetch, out=None, on_device=False):
+        outs = []
+        for lo in range(0, n, self.max_batch):
+            f = fetch(lo, min(n, lo + self.max_batch))
+            self.fetched.append(int(f["query_ids"].shape[0]))
+            # integers only: independent of the chunking; depends on every decoded array and on the query text
+            s = (f["feats"].double().mul(64).round().long().sum(dim=(1, 2)) + f["label_ids"].long().sum(dim=(1, 2)) * 3
+                 + f["query_ids"].long().sum(1) * 7) % 1000
+            outs.append(torch.stack([1.0 - s.float() / 1000.0, s.float() / 1000.0], 1))
+        return torch.cat(outs) if outs else torch.empty((0, 2))
+
+
+def _tsv_worker(rank, world, port, n, out_dir):
+    """drivers.score_tsv on two gloo ranks: every rank decodes only its own lines (one chunk ahead, on the helper
+    thread, three decoders in rotation) and all ranks end with the scores of the whole file in file order."""
+    import json
+
+    from kddcup_2020_multimodalitiesrecall_2nd_place_b200 import drivers, tokenizer
+    from kddcup_2020_multimodalitiesrecall_2nd_place_b200.config import LDS, ModelConfig
+    from tests.test_widening_host import _make_lines
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        kat = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "tokenizer_kat.json"), encoding="utf-8"))
+        vocab = {t: i for i, t in enumerate(dict.fromkeys(kat["vocab"]))}
+        tok = tokenizer.FullTokenizer(vocab=vocab)
+        labels = {i: "women dress" for i in range(33)}
+        lines, _ = _make_lines(n, np.random.default_rng(5), max_nb=12)
+        cfg = ModelConfig(LDS, n_layers=1, lq=20, nbox=10, vocab=len(vocab))
+        whole = drivers.score_tsv(_StandInTsvScorer(cfg), tok, labels, lines)          # one rank, the whole file
+        sc = _StandInTsvScorer(cfg)
+        got = drivers.score_tsv(sc, tok, labels, lines, rank=rank, world=world)
+        lo, hi, _ = shard_range(n, rank, world)
+        assert sum(sc.fetched) == hi - lo and all(0 < c <= sc.max_batch for c in sc.fetched)
+        assert np.array_equal(got["score"], whole["score"]) and len(got["score"]) == n
+        assert got["query_id"].tolist() == [7 * i for i in range(n)] and got["product_id"].tolist() == [1000 + i for i in range(n)]
+        np.save(os.path.join(out_dir, f"tsv_{rank}.npy"), got["score"])
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [23, 8, 1])
+def test_two_gloo_ranks_score_a_tsv_through_the_driver(n, tmp_path):
+    mp.spawn(_tsv_worker, args=(2, _free_port(), n, str(tmp_path)), nprocs=2, join=True)
+    assert np.array_equal(np.load(tmp_path / "tsv_0.npy"), np.load(tmp_path / "tsv_1.npy"))
+
+
 def test_shard_range_covers_every_pair_once():
     for n in (0, 1, 7, 30000, 10001):
         for world in (1, 2, 4, 8):
