@@ -148,6 +148,7 @@ cls_pool_head_kernel(const float* __restrict__ y32, const float* __restrict__ ga
   __shared__ float gather[kPhCtas][kPhRows][3];       // meaningful in the cluster's CTA 0
   pdl_wait();
   pdl_launch_dependents();
+  cluster_arrive_relaxed();     // "this CTA runs": waited for below, before anything is stored into CTA 0's `gather`
   const uint32_t rank = cluster_ctarank();
   const int row0 = int(blockIdx.x / kPhCtas) * kPhRows;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -259,6 +260,7 @@ cls_pool_head_kernel(const float* __restrict__ y32, const float* __restrict__ ga
       if (lane == 0) part[warp][r][c] = t;
     }
   __syncthreads();
+  cluster_wait();               // every CTA of the cluster has started: CTA 0's shared memory may be written
   if (threadIdx.x < kPhRows * 3) {
     const int r = threadIdx.x / 3, c = threadIdx.x % 3;
     float t = 0.f;
